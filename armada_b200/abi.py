@@ -158,6 +158,7 @@ class RoundStats(C.Structure):
         ("tree_rescans", C.c_uint64),
         ("gpu_launches", C.c_uint64),
         ("device_ms", C.c_double),
+        ("schedule_pass_ms", C.c_double),
     ]
 
 

@@ -1,0 +1,134 @@
+// armada_dev.h — device-side data layout of one scheduling round (sm_100a).
+//
+// HBM layout (all SoA, resource-major so a warp reads consecutive nodes):
+//   alloc      [PL][D][N] int64   Node.AllocatableByPriority (internaltypes/node.go:57).  Nodes are
+//                                 stored in NODE-ID ORDER (device index == id rank) and indexed
+//                                 resources are held in units of their index resolution, so the
+//                                 best-fit key of nodedb/encoding.go:37-58 is a pure bit-pack.
+//   total      [D][N]  int64      Node.totalResources (same units)
+//   node_sclass[N]     u32        static class (taints/labels) id → column of static_match
+//   jobs       SoA over J         class / queue / gang / order rank / run binding
+//   per-job round state           bound node, evicted flag, scheduled-at priority, qctx set
+//                                 membership, pod scheduling result
+// The persistent round kernel keeps per-queue DRF state and the best-fit tournament trees
+// in shared memory (see armada_round.cu).
+#pragma once
+#include <stdint.h>
+
+#include "armada_b200.h"
+
+#define ARMADA_DEV_MAX_QUEUES 128
+#define ARMADA_DEV_MAX_SLOTS 32
+#define ARMADA_DEV_VARIANTS (1 + ARMADA_MAX_AWAY)  // home + away node types per class
+
+struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
+  int32_t D, R, PL, PC, Q, C, T, S, rows;
+  uint32_t N, J, G;
+  int32_t indexed_resource[ARMADA_MAX_RESOURCES];
+  int64_t res_scale[ARMADA_MAX_RESOURCES];  // per FACTORY resource: index resolution or 1
+  int32_t key_shift[ARMADA_MAX_RESOURCES];  // per indexed resource i: bit position in the packed key
+  int32_t node_bits;                        // low bits of the key hold the node (id-rank) index
+  int32_t priorities[ARMADA_MAX_PRIORITIES];
+  ArmadaPriorityClass pcs[ARMADA_MAX_PRIORITY_CLASSES];
+  int64_t total_resources[ARMADA_MAX_RESOURCES];
+  double drf_mult[ARMADA_MAX_RESOURCES];
+  int64_t max_to_schedule[ARMADA_MAX_RESOURCES];
+  uint8_t has_round_limit, protect_uncapped, prefer_large, disable_home, disable_away, disable_gang_away,
+      global_inf, _pad;
+  double protected_fraction;
+  uint32_t max_lookback, disallowed_mask;
+  double global_tokens;
+  int64_t global_burst;
+  int32_t tile_shift;  // leaf tile = 1 << tile_shift nodes
+  int32_t num_tiles, num_groups, num_slots, sw, tw;
+};
+
+struct DevPtrs {
+  // ---- immutable snapshot (uploaded once per round input) ----
+  const int64_t* node_total;       // [D][N]
+  const int64_t* node_allocatable; // [D][N]
+  const uint32_t* node_sclass;     // [N]
+  const uint8_t* node_flags;       // [N]
+  const int64_t* class_req_raw;    // [C][D] factory units (queue / DRF accounting)
+  const int64_t* class_req_node;   // [C][D] node units (indexed resources ÷ resolution)
+  const uint32_t* class_pc;        // [C]
+  const uint32_t* class_row;       // [C][VARIANTS] static row per variant (ARMADA_NONE = absent)
+  const uint8_t* class_key_valid;  // [C]
+  const uint32_t* static_match;    // [rows][sw]
+  const uint32_t* job_class;       // [J]
+  const uint32_t* job_queue;       // [J]
+  const uint32_t* job_gang;        // [J]
+  const uint32_t* job_node0;       // [J] run binding at round start (device node index)
+  const int32_t* job_sap0;         // [J] run's scheduled-at priority or ARMADA_NO_PRIORITY
+  const uint32_t* job_rank;        // [J] rank under SchedulingOrderCompare (unique)
+  const uint32_t* gang_card;       // [G] declared cardinality
+  const uint32_t* gang_count;      // [G] active members in this input
+  const uint32_t* gang_off;        // [G+1] CSR offsets into gang_buf
+  const uint32_t* queued_start;    // [Q+1]
+  const uint32_t* queued_order;    // [#queued]
+  const double* queue_weight;      // [Q]
+  const uint8_t* queue_cordoned;   // [Q]
+  const int64_t* queue_alloc_pc0;  // [Q][PC][D]
+  const int64_t* queue_cdemand;    // [Q][D]
+  const int64_t* queue_penalty;    // [Q][D]
+  const uint8_t* queue_has_limit;  // [Q][PC]
+  const int64_t* queue_limit;      // [Q][PC][D]
+  const double* queue_tokens0;     // [Q]
+  const int64_t* queue_burst;      // [Q]
+  const uint8_t* queue_inf;        // [Q]
+  // ---- mutable round state ----
+  int64_t* alloc;                  // [PL][D][N]
+  uint32_t* bound_node;            // [J]
+  uint8_t* evicted_on_node;        // [J] Node.EvictedJobRunIds
+  int32_t* sched_prio;             // [J] scheduledAtPriorityByJobId (ARMADA_NO_PRIORITY = absent)
+  uint8_t* q_successful;           // [J] qctx.SuccessfulJobSchedulingContexts
+  uint8_t* q_unsuccessful;         // [J]
+  uint8_t* q_rescheduled;          // [J]
+  uint8_t* q_evicted;              // [J] qctx.EvictedJobsById
+  uint8_t* q_reason;               // [J]
+  uint8_t* jc_evicted;             // [J] job is carried by an evicted jctx this pass
+  uint32_t* jc_card;               // [J] jctx.CurrentGangCardinality
+  uint32_t* assigned_node;         // [J] jctx.AssignedNode of the evicted jctx
+  uint8_t* in_preempted;           // [J] preemptedJobsById
+  uint8_t* in_scheduled;           // [J] scheduledJobsById
+  uint8_t* in_sae;                 // [J] scheduledAndEvictedJobsById
+  uint8_t* ev_mark;                // [J] evicted by the evictor currently running
+  uint8_t* gang_ev;                // [G] gang has >=1 evicted member (current evictor)
+  uint8_t* has_pctx;               // [J]
+  uint32_t* res_node;              // [J] pctx.NodeId
+  int32_t* res_sched_at;           // [J]
+  int32_t* res_preempted_at;       // [J]
+  uint8_t* res_method;             // [J]
+  uint32_t* gang_fill;             // [G] members gathered so far by the gang iterator
+  uint32_t* gang_buf;              // [sum gang_count] members in arrival order
+  int32_t* ev_index_of_job;        // [J] "evictedJobs" table: index or -1
+  uint32_t* ev_job_by_index;       // [J]
+  uint8_t* ev_alive;               // [J]
+  uint32_t* evq_start;             // [Q+1] evicted jobs per queue (sorted) for the current pass
+  uint32_t* evq_jobs;              // [J]
+  uint64_t* sort_keys;             // [J] scratch
+  uint64_t* sort_keys2;            // [J]
+  uint32_t* sort_vals;             // [J]
+  uint32_t* sort_vals2;            // [J]
+  uint32_t* counters;              // [16] misc device counters (evicted count, …)
+  uint8_t* unfeasible;             // [C] UnfeasibleSchedulingKeys: reason or 0
+  int16_t* slot_of;                // [C*VARIANTS*PL] tree slot, -1 none yet, -2 uncached
+  uint32_t* slot_static;           // [slots][ceil(N/32)] static-ok bitmap per slot
+  uint32_t* undo_log;              // [4 * J] txn undo records
+  // fair preemption scratch
+  int64_t* fp_avail;               // [D][N]
+  uint32_t* fp_epoch;              // [N]
+  uint32_t* fp_head;               // [N] most recent visited evicted index on the node
+  uint32_t* fp_next;               // [J] chain by evicted index
+  uint8_t* fp_bad;                 // [N] static requirements not met (valid when epoch matches)
+  // ---- queue / sctx state persisted between kernels ----
+  int64_t* q_alloc;                // [Q][D]
+  int64_t* q_alloc_pc;             // [Q][PC][D]
+  double* q_fair;                  // [Q][3]
+  double* q_tokens;                // [Q]
+  int64_t* s_scheduled;            // [D]
+  int64_t* s_evicted;              // [D]
+  int64_t* s_counts;               // [8]: 0 numScheduledJobs 1 numScheduledGangs 2 numEvictedJobs
+                                   //      3 termination(pass1) 4 global tokens (double bits)
+  unsigned long long* stats;       // [8]: loop iters, probes, placements, fair scans, rescans
+};

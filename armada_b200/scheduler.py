@@ -1,0 +1,86 @@
+"""Reference-shaped entry point for one scheduling round, backed ONLY by the CUDA library.
+
+Mirrors `scheduling.NewPreemptingQueueScheduler(...).Schedule(ctx)`
+(scheduling/preempting_queue_scheduler.go:50-84,84-285): the caller hands over the round's
+SchedulingContext / NodeDb / job view (already flattened into an `ArmadaRoundInput`) and gets
+back scheduled / preempted jobs plus the updated accounting.  There is no CPU fallback: if
+libarmada_b200.so or a CUDA device is missing this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+from . import abi
+from .model import RoundResult
+
+
+class DeviceRound:
+    """Owns one `ArmadaRound*` (device context).  upload → run → download, like
+    populateNodeDb → Schedule → result read-back in scheduling_algo.go:740-840."""
+
+    def __init__(self, device: int = 0):
+        self.lib = abi.load_product()
+        self.h = C.c_void_p()
+        self._check(self.lib.armada_round_create(device, C.byref(self.h)))
+        self._input: Optional[abi.RoundInput] = None
+
+    def _check(self, status: int):
+        if status != abi.OK:
+            raise abi.ArmadaError(status, f"{self.lib.armada_strerror(status).decode()}: {self.lib.armada_last_error().decode()}")
+
+    def upload(self, inp: abi.RoundInput) -> None:
+        self._check(self.lib.armada_round_upload(self.h, C.byref(inp)))
+        self._input = inp
+
+    def run(self) -> abi.RoundStats:
+        stats = abi.RoundStats()
+        self._check(self.lib.armada_round_run(self.h, C.byref(stats)))
+        return stats
+
+    def download(self, res: Optional[RoundResult] = None) -> RoundResult:
+        if res is None:
+            res = RoundResult(self._input)
+        self._check(self.lib.armada_round_download(self.h, C.byref(res.out)))
+        return res
+
+    def schedule(self, inp: abi.RoundInput, res: Optional[RoundResult] = None) -> RoundResult:
+        """Host buffers in, host buffers out (the end-to-end call a Go shim makes per pool)."""
+        if res is None:
+            res = RoundResult(inp)
+        self._input = inp
+        self._check(self.lib.armada_round_schedule(self.h, C.byref(inp), C.byref(res.out), C.byref(res.stats)))
+        return res
+
+    def close(self):
+        if self.h:
+            self.lib.armada_round_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PreemptingQueueScheduler:
+    """`sch := NewPreemptingQueueScheduler(sctx, constraints, …, jobRepo, nodeDb, …); sch.Schedule(ctx)`"""
+
+    def __init__(self, round_input: abi.RoundInput, device: int = 0):
+        self.round_input = round_input
+        self.device = device
+
+    def schedule(self) -> RoundResult:
+        with DeviceRound(self.device) as r:
+            return r.schedule(self.round_input)
+
+
+def round_schedule(inp: abi.RoundInput, device: int = 0) -> RoundResult:
+    return PreemptingQueueScheduler(inp, device).schedule()

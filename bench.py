@@ -1,0 +1,318 @@
+#!/usr/bin/env python3
+"""bench.py — job-placements/sec per scheduling round (BASELINE.json metric).
+
+A "step" is one full PreemptingQueueScheduler.Schedule round (evict → schedule → oversubscribed
+evict → re-schedule → unbind) over one synthetic pool.  Default workload is the configuration the
+metric is quoted on: C3 = 100k nodes × 1M queued jobs × 64 queues (it fits one GPU).
+
+  value  : whole-job placements/s with the round's inputs already resident in HBM
+           (armada_round_run only; CUDA events on the launching stream; max over ranks)
+  e2e    : the same metric through the reference-facing C-ABI call armada_round_schedule with
+           HOST buffers on both sides (pinned host → device upload, run, device → host results)
+  roofline: dominant kernel k_schedule_pass; achieved = probes × N × (8·D+4) algorithmic bytes
+            ÷ its CUDA-event duration, against the measured HBM copy bandwidth
+  cpu_baseline: the C++ restatement of the reference round (oracle "port"), 1 host core
+
+Multi-GPU (torchrun, one rank per GPU): pools are independent units in the reference
+(scheduling_algo.go:129-160), so rank r schedules its own pool (same shape, seed+r); no
+data-path collective; results are counted with one all-reduce.  scaling = "weak".
+
+`--impl reference` times the oracle port on the host cores instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "job-placements/sec per scheduling round; 100k nodes x 1M jobs"
+UNIT = "placements/s"
+
+
+def make_workload(name: str, seed_offset: int = 0):
+    from armada_b200 import synth
+    if name == "C3":
+        return synth.config_c3(seed=synth.SEED + seed_offset)
+    if name == "C2":
+        return synth.config_c2()
+    if name == "C4":
+        return synth.config_c4(seed=synth.SEED + seed_offset)
+    if name == "C5":
+        return synth.config_c5(seed=synth.SEED + seed_offset)
+    if name == "C1":
+        return synth.config_c1()
+    if name.startswith("C3@"):  # scaled C3 (bounded CPU sample)
+        return synth.scaled("C3", float(name.split("@")[1]))
+    raise SystemExit(f"unknown workload {name}")
+
+
+def workload_config(name, inp, n_gpus):
+    return {
+        "workload": name,
+        "nodes": int(inp.num_nodes), "queues": int(inp.num_queues), "jobs": int(inp.num_jobs),
+        "resources": int(inp.num_resources), "priority_levels": int(inp.num_priorities),
+        "pools": n_gpus, "parallelism": f"pool-per-gpu x{n_gpus}",
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("k_schedule_pass_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(name: str, budget_s: float = 20.0):
+    """Oracle port timed on ONE host core (the reference round is single-goroutine) on a bounded
+    sample: the full workload if the oracle finishes it within the budget, else a scaled C3."""
+    import oracle_lib
+    t0 = time.perf_counter()
+    r = make_workload(name)
+    inp = r.to_input()
+    res = oracle_lib.round_schedule(inp)  # warm (page-in, allocator)
+    t = time.perf_counter()
+    res = oracle_lib.round_schedule(inp)
+    dt = time.perf_counter() - t
+    placed = int(res.stats.placements)
+    reps = 1
+    while time.perf_counter() - t0 < budget_s and reps < 5:
+        t = time.perf_counter()
+        res = oracle_lib.round_schedule(inp)
+        dt = min(dt, time.perf_counter() - t)
+        reps += 1
+    return {"value": placed / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{name} full round ({inp.num_nodes} nodes x {inp.num_jobs} jobs), best of {reps} runs, {dt:.3f} s/round, "
+                      f"C++ restatement of the reference (Go toolchain unavailable)", "placements": placed, "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    import oracle_lib
+    r = make_workload(name)
+    inp = r.to_input()
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle_lib.round_schedule(inp)
+    steps = max(1, min(args.steps, 3))
+    t = time.perf_counter()
+    placed = 0
+    for _ in range(steps):
+        res = oracle_lib.round_schedule(inp)
+        placed += int(res.stats.placements)
+    dt = time.perf_counter() - t
+    val = placed / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+        "config": workload_config(name, inp, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{name} full round x{steps}; C++ restatement of the reference scheduler "
+                                   f"(single-goroutine algorithm ⇒ 1 core; Go toolchain unavailable here)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from armada_b200.model import RoundResult
+    from armada_b200.scheduler import DeviceRound
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    r = make_workload(args.workload, seed_offset=rank)
+    inp = r.to_input()
+    # pin the host input buffers (H2D from pinned memory)
+    rt = torch.cuda.cudart()
+    for a in r._keep:
+        if a.nbytes:
+            rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+    h2d = r.h2d_bytes()
+    dev = DeviceRound(local)
+    res = RoundResult(inp)
+    for name in RoundResult.ARRAYS:
+        a = getattr(res, name)
+        if a.nbytes:
+            rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+    d2h = sum(getattr(res, n).nbytes for n in ("job_state", "job_node", "job_scheduled_at_priority", "job_preempted_at_priority",
+                                               "job_method", "job_reason", "node_alloc", "queue_allocated",
+                                               "queue_allocated_by_pc", "queue_fair_share"))
+    flush = torch.empty(256 * 2**20, dtype=torch.uint8, device="cuda")
+
+    dev.upload(inp)
+    for _ in range(args.warmup):
+        flush.zero_()
+        stats = dev.run()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms, pass_ms, placements, probes, launches = 0.0, 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        stats = dev.run()  # timed on the device: CUDA events on the launching stream
+        dev_ms += stats.device_ms
+        pass_ms += stats.schedule_pass_ms
+        placements += int(stats.placements)
+        probes += int(stats.probes)
+        launches += int(stats.gpu_launches)
+    barrier()
+    # end-to-end: host buffers in, host buffers out, every step
+    e2e_s = 0.0
+    e2e_placed = 0
+    for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        out = dev.schedule(inp, res)
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t
+        e2e_placed += int(out.stats.placements)
+    barrier()
+    clocks = sampler.stop()
+    final = dev.download(res)
+
+    tm = torch.tensor([dev_ms, e2e_s * 1e3, pass_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([placements, e2e_placed, probes, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    tm, cnt = tm.cpu().numpy(), cnt.cpu().numpy()
+    if rank == 0:
+        value = cnt[0] / (tm[0] / 1e3)
+        e2e_value = cnt[1] / (tm[1] / 1e3)
+        N, Dn = int(inp.num_nodes), int(inp.num_resources)
+        probe_bytes = N * (8 * Dn + 4)
+        peak, peak_src = measured_peak()
+        local_probes = probes
+        achieved = (local_probes * probe_bytes) / (pass_ms / 1e3) / 1e9 if pass_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tm[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args.workload, inp, world),
+            "placements_per_round": int(placements / args.steps),
+            "gpu_launches": int(cnt[3]),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": tm[1] / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "k_schedule_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "algorithmic_bytes_per_probe": probe_bytes, "probes_per_launch": int(local_probes / args.steps),
+                         "kernel_ms_per_launch": pass_ms / args.steps,
+                         "kernel_share_of_step": pass_ms / dev_ms if dev_ms else None,
+                         "note": "smarter-than-scan (tournament trees): >1.0 means faster than re-scanning every node per probe"},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

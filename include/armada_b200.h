@@ -240,6 +240,8 @@ typedef struct {
   uint64_t tree_rescans;         /* device only: leaf-tile rescans                            */
   uint64_t gpu_launches;         /* device only: kernels launched by armada_round_run         */
   double device_ms;              /* device only: CUDA-event time of armada_round_run          */
+  double schedule_pass_ms;       /* device only: CUDA-event time of the persistent schedule-pass
+                                    kernel launches (the dominant kernel) inside device_ms    */
 } ArmadaRoundStats;
 
 /* ---- product entry points (libarmada_b200.so) ------------------------------------- */

@@ -1,0 +1,143 @@
+"""Parity tests proper: the CUDA path (through the C ABI, host buffers in/out) against the CPU
+oracle on the same inputs — bit-exact on every output array (job outcomes, nodes, priorities,
+methods, reasons, final NodeDb allocatable vectors, per-queue accounting, fair-share doubles,
+counters).  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import go_tables as gt
+import oracle_lib
+from armada_b200 import abi, synth
+from armada_b200.scheduler import DeviceRound
+
+pytestmark = pytest.mark.gpu
+
+_dev = None
+
+
+def device():
+    global _dev
+    if _dev is None:
+        _dev = DeviceRound(0)
+    return _dev
+
+
+def cuda_round(inp):
+    return device().schedule(inp)
+
+
+def assert_parity(inp, label=""):
+    want = oracle_lib.round_schedule(inp)
+    got = cuda_round(inp)
+    bad = got.diff(want)
+    assert not bad, f"{label}: CUDA != oracle:\n  " + "\n  ".join(bad)
+    return got, want
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_rounds(seed):
+    r = synth.random_round(
+        seed,
+        away=(seed % 4 == 1),
+        round_limit=(seed % 6 == 3),
+        queue_limits=(seed % 6 == 4),
+        protected_fraction=0.5 if seed % 3 == 2 else 0.0,
+        lookback=40 if seed % 5 == 1 else 0,
+        n_nodes=40 + 13 * (seed % 7),
+        n_jobs=300 + 50 * (seed % 5),
+        n_running=80 + 20 * (seed % 4),
+    )
+    got, _ = assert_parity(r.to_input(), r.name)
+    assert got.stats.gpu_launches > 0
+
+
+@pytest.mark.parametrize("seed", range(100, 108))
+def test_random_rounds_many_nodes(seed):
+    # > 1 tile group (N > 4096) so every tree level is exercised
+    r = synth.random_round(seed, n_nodes=5000 + 700 * (seed % 3), n_queues=9, n_jobs=6000, n_running=3000,
+                           protected_fraction=0.5 if seed % 2 else 0.0)
+    assert_parity(r.to_input(), r.name)
+
+
+@pytest.mark.parametrize("name,scale", [("C2", 0.02), ("C3", 0.004), ("C4", 0.006), ("C5", 0.004), ("C3", 0.05), ("C5", 0.03)])
+def test_scaled_configs(name, scale):
+    r = synth.scaled(name, scale)
+    got, want = assert_parity(r.to_input(), f"{name}@{scale}")
+    assert got.out.num_result_scheduled == want.out.num_result_scheduled
+
+
+def test_c1_simulator_config():
+    got, want = assert_parity(synth.config_c1().to_input(), "C1")
+    assert got.out.num_result_scheduled == 1000
+
+
+PQS = gt.load_cases("preempting_queue_scheduler")
+QS = gt.load_cases("queue_scheduler")
+
+
+def _cuda_round_or_skip(inp):
+    try:
+        got = cuda_round(inp)
+    except abi.ArmadaError as e:
+        if e.status == abi.E_UNSUPPORTED:
+            raise gt.UnsupportedCase(str(e))
+        raise
+    want = oracle_lib.round_schedule(inp)
+    bad = got.diff(want)
+    assert not bad, "CUDA != oracle:\n  " + "\n  ".join(bad)
+    return got
+
+
+@pytest.mark.parametrize("name", sorted(PQS.keys()))
+def test_reference_pqs_tables_on_device(name):
+    """The reference's own TestPreemptingQueueScheduler scenarios, driven through the CUDA path."""
+    try:
+        gt.run_pqs_case(PQS[name], _cuda_round_or_skip)
+    except gt.UnsupportedCase as e:
+        pytest.skip(f"outside device domain / not modelled: {e}")
+
+
+@pytest.mark.parametrize("name", sorted(QS.keys()))
+def test_reference_queue_scheduler_tables_on_device(name):
+    try:
+        gt.run_queue_scheduler_case(QS[name], _cuda_round_or_skip)
+    except gt.UnsupportedCase as e:
+        pytest.skip(f"outside device domain / not modelled: {e}")
+
+
+def test_unsupported_domain_fails_loudly():
+    r = synth.random_round(1)
+    r.class_request = r.class_request.copy()
+    r.class_request[0, synth.CPU] = 1500  # not a multiple of the 1-cpu index resolution
+    with pytest.raises(abi.ArmadaError) as ei:
+        cuda_round(r.to_input())
+    assert ei.value.status == abi.E_UNSUPPORTED
+
+
+def test_full_size_properties():
+    """BASELINE-size C3 through size-independent properties: no oversubscription, every scheduled
+    job fits its node, conservation of resources, idempotence of a second run."""
+    r = synth.config_c3()
+    inp = r.to_input()
+    dev = device()
+    dev.upload(inp)
+    dev.run()
+    a = dev.download()
+    dev.run()
+    b = dev.download()
+    assert not a.diff(b), "armada_round_run is not idempotent"
+    N = inp.num_nodes
+    assert (a.node_alloc >= 0).all()
+    sched = a.job_state == abi.JOB_SCHEDULED
+    assert sched.sum() == a.out.num_result_scheduled > 0
+    req = r.class_request[np.asarray(r.job_class).astype(np.int64)]
+    used = np.zeros((synth.D, N), np.int64)
+    np.add.at(used.T, a.job_node[sched].astype(np.int64), req[sched])
+    assert (used + a.node_alloc[0] == r.node_allocatable).all()
+    # gpu jobs only on gpu nodes
+    gpu_jobs = sched & (req[:, synth.GPU] > 0)
+    assert (np.asarray(r.node_static_class)[a.job_node[gpu_jobs].astype(np.int64)] == 1).all()
+    # queue accounting equals the sum of scheduled requests
+    qa = np.zeros_like(a.queue_allocated)
+    np.add.at(qa, np.asarray(r.job_queue).astype(np.int64)[sched], req[sched])
+    assert (qa == a.queue_allocated).all()
