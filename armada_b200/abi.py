@@ -132,6 +132,7 @@ class RoundOutput(C.Structure):
         ("job_preempted_at_priority", i32p),
         ("job_method", u8p),
         ("job_reason", u8p),
+        ("job_seq", u32p),
         ("node_alloc", i64p),
         ("queue_allocated", i64p),
         ("queue_allocated_by_pc", i64p),
@@ -159,6 +160,7 @@ class RoundStats(C.Structure):
         ("gpu_launches", C.c_uint64),
         ("device_ms", C.c_double),
         ("schedule_pass_ms", C.c_double),
+        ("phase_cycles", C.c_uint64 * 8),
     ]
 
 

@@ -14,6 +14,7 @@
 // in shared memory (see armada_round.cu).
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 #include "armada_b200.h"
 
@@ -41,6 +42,10 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int64_t global_burst;
   int32_t tile_shift;  // leaf tile = 1 << tile_shift nodes
   int32_t num_tiles, num_groups, num_slots, sw, tw;
+  // shared-memory layout of k_schedule_pass (byte offsets from the dynamic smem base)
+  int32_t win_w;       // stream-window records per queue (power of two, <= 32)
+  int32_t nc_entries;  // node-cache entries (power of two)
+  uint32_t off_cls, off_win, off_nc_tag, off_nc_val, off_root, off_l2, off_leaf;
 };
 
 struct DevPtrs {
@@ -54,6 +59,9 @@ struct DevPtrs {
   const uint32_t* class_pc;        // [C]
   const uint32_t* class_row;       // [C][VARIANTS] static row per variant (ARMADA_NONE = absent)
   const uint8_t* class_key_valid;  // [C]
+  const double* class_cost;        // [C] DRF UnweightedCostFromAllocation(request)
+  const uint4* q_rec;              // [#queued] stream records aligned with queued_order
+  uint4* ev_rec;                   // [J] stream records aligned with evq_jobs (per pass)
   const uint32_t* static_match;    // [rows][sw]
   const uint32_t* job_class;       // [J]
   const uint32_t* job_queue;       // [J]
@@ -99,6 +107,7 @@ struct DevPtrs {
   int32_t* res_sched_at;           // [J]
   int32_t* res_preempted_at;       // [J]
   uint8_t* res_method;             // [J]
+  uint32_t* res_seq;               // [J] loop iteration of the job's last gang attempt
   uint32_t* gang_fill;             // [G] members gathered so far by the gang iterator
   uint32_t* gang_buf;              // [sum gang_count] members in arrival order
   int32_t* ev_index_of_job;        // [J] "evictedJobs" table: index or -1
@@ -114,7 +123,7 @@ struct DevPtrs {
   uint8_t* unfeasible;             // [C] UnfeasibleSchedulingKeys: reason or 0
   int16_t* slot_of;                // [C*VARIANTS*PL] tree slot, -1 none yet, -2 uncached
   uint32_t* slot_static;           // [slots][ceil(N/32)] static-ok bitmap per slot
-  uint32_t* undo_log;              // [4 * J] txn undo records
+  uint32_t* undo_log;              // [5 * J] txn undo records
   // fair preemption scratch
   int64_t* fp_avail;               // [D][N]
   uint32_t* fp_epoch;              // [N]

@@ -670,6 +670,7 @@ class RoundInputBuilder:
             self.queued_order = a(order or [0], np.uint32)
             inp.queued_start = self._ptr(self.queued_start, C.c_uint32)
             inp.queued_order = self._ptr(self.queued_order, C.c_uint32)
+        inp._keepalive = self._keep
         self.input = inp
 
 
@@ -685,6 +686,7 @@ class RoundResult:
         self.job_preempted_at_priority = np.zeros(J, np.int32)
         self.job_method = np.zeros(J, np.uint8)
         self.job_reason = np.zeros(J, np.uint8)
+        self.job_seq = np.zeros(J, np.uint32)
         self.node_alloc = np.zeros((PL, D, N), np.int64)
         self.queue_allocated = np.zeros((Q, D), np.int64)
         self.queue_allocated_by_pc = np.zeros((Q, PC, D), np.int64)
@@ -698,6 +700,7 @@ class RoundResult:
         o.job_preempted_at_priority = self.job_preempted_at_priority.ctypes.data_as(abi.i32p)
         o.job_method = self.job_method.ctypes.data_as(abi.u8p)
         o.job_reason = self.job_reason.ctypes.data_as(abi.u8p)
+        o.job_seq = self.job_seq.ctypes.data_as(abi.u32p)
         o.node_alloc = self.node_alloc.ctypes.data_as(abi.i64p)
         o.queue_allocated = self.queue_allocated.ctypes.data_as(abi.i64p)
         o.queue_allocated_by_pc = self.queue_allocated_by_pc.ctypes.data_as(abi.i64p)
@@ -709,7 +712,7 @@ class RoundResult:
         self.num_jobs = inp.num_jobs
 
     ARRAYS = ("job_state", "job_node", "job_scheduled_at_priority", "job_preempted_at_priority", "job_method",
-              "job_reason", "node_alloc", "queue_allocated", "queue_allocated_by_pc", "queue_fair_share",
+              "job_reason", "job_seq", "node_alloc", "queue_allocated", "queue_allocated_by_pc", "queue_fair_share",
               "scheduled_resources", "evicted_resources")
     SCALARS = ("num_scheduled_jobs", "num_scheduled_gangs", "num_evicted_jobs", "termination_reason",
                "num_result_scheduled", "num_result_preempted")

@@ -205,6 +205,7 @@ class RawRound:
         inp.queue_limiter_tokens = ptr(arr(np.full(Q, float(2**62)), np.float64), C.c_double)
         inp.queue_limiter_burst = ptr(arr(np.full(Q, 2**62), np.int64), C.c_int64)
         inp.queue_limiter_is_inf = ptr(arr(np.ones(Q), np.uint8), C.c_uint8)
+        inp._keepalive = self._keep  # the struct only holds raw pointers into these arrays
         self.input = inp
         return inp
 

@@ -228,16 +228,22 @@ def main():
     inp = r.to_input()
     # pin the host input buffers (H2D from pinned memory)
     rt = torch.cuda.cudart()
+
+    def pin(a):
+        # page-granular: only large buffers are registered (small ones share pages)
+        if a.nbytes >= (1 << 20):
+            try:
+                rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+            except Exception:
+                pass
+
     for a in r._keep:
-        if a.nbytes:
-            rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+        pin(a)
     h2d = r.h2d_bytes()
     dev = DeviceRound(local)
     res = RoundResult(inp)
     for name in RoundResult.ARRAYS:
-        a = getattr(res, name)
-        if a.nbytes:
-            rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+        pin(getattr(res, name))
     d2h = sum(getattr(res, n).nbytes for n in ("job_state", "job_node", "job_scheduled_at_priority", "job_preempted_at_priority",
                                                "job_method", "job_reason", "node_alloc", "queue_allocated",
                                                "queue_allocated_by_pc", "queue_fair_share"))
@@ -295,6 +301,9 @@ def main():
             "ms_per_step": tm[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args.workload, inp, world),
             "placements_per_round": int(placements / args.steps),
+            "control_warp_cycles_per_iteration": {n: round(int(stats.phase_cycles[i]) / max(1, int(stats.loop_iterations)), 1) for i, n in enumerate(
+                ("queue_argmin", "gang_total", "node_select", "node_row_update", "tree_refresh_wait", "result_algebra", "iterator_advance", "clear_total"))},
+            "loop_iterations_per_round": int(stats.loop_iterations),
             "gpu_launches": int(cnt[3]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

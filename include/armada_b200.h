@@ -216,6 +216,9 @@ typedef struct {
   int32_t* job_preempted_at_priority; /* [J] pctx.PreemptedAtPriority                          */
   uint8_t* job_method;           /* [J] ARMADA_METHOD_*                                        */
   uint8_t* job_reason;           /* [J] ARMADA_REASON_* for FAILED jobs                        */
+  uint32_t* job_seq;             /* [J] 1-based QueueScheduler loop iteration (over both passes)
+                                    of the job's last scheduling attempt, 0 = never attempted
+                                    (QueueStats-style observability; also pins the ORDER)     */
   int64_t* node_alloc;           /* [PL][D][N] AllocatableByPriority after the round          */
   int64_t* queue_allocated;      /* [Q][D] qctx.Allocated after the round                     */
   int64_t* queue_allocated_by_pc;/* [Q][PC][D]                                                */
@@ -242,6 +245,10 @@ typedef struct {
   double device_ms;              /* device only: CUDA-event time of armada_round_run          */
   double schedule_pass_ms;       /* device only: CUDA-event time of the persistent schedule-pass
                                     kernel launches (the dominant kernel) inside device_ms    */
+  uint64_t phase_cycles[8];      /* device only: SM clock cycles the control warp spent in
+                                    0 queue arg-min, 1 gang bookkeeping+constraints, 2 node
+                                    selection, 3 node row update, 4 tree refresh wait,
+                                    5 result algebra, 6 iterator advance, 7 cost update       */
 } ArmadaRoundStats;
 
 /* ---- product entry points (libarmada_b200.so) ------------------------------------- */

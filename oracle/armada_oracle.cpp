@@ -702,6 +702,7 @@ struct Round {
   size_t num_unfeasible = 0;
   // latest pod scheduling result per job (the jctx the result lists would carry)
   std::vector<JobCtx> last_jctx;
+  std::vector<uint32_t> job_seq;  // loop iteration of the job's last gang attempt
   std::vector<std::vector<uint32_t>> queued_by_queue;
   ArmadaRoundStats stats{};
   std::vector<std::vector<uint32_t>> gang_members;  // jobRepo.GetGangJobsByGangId
@@ -721,6 +722,7 @@ struct Round {
     evicted_resources.assign(D, 0);
     unfeasible_key.assign(C, 0);
     last_jctx.resize(J);
+    job_seq.assign(J, 0);
     global_tokens = in->global_limiter_tokens;
     gang_members.resize(in->num_gangs);
     for (uint32_t j = 0; j < J; ++j)
@@ -1253,6 +1255,7 @@ struct Round {
       if (top < 0) break;
       Gang g = ci.items[(size_t)top].it->next;  // Peek
       ++stats.loop_iterations;
+      for (JobCtx* jc : g.jctxs) job_seq[jc->job] = (uint32_t)stats.loop_iterations;
       uint8_t reason = ARMADA_REASON_NONE;
       bool ok = gang_schedule(g, skip_key_check, &reason);
       candidate_clear(ci);
@@ -1514,6 +1517,7 @@ struct Round {
       if (out->job_preempted_at_priority) out->job_preempted_at_priority[j] = has ? jc.p_preempted_at : ARMADA_NO_PRIORITY;
       if (out->job_method) out->job_method[j] = has ? jc.p_method : (uint8_t)ARMADA_METHOD_NONE;
       if (out->job_reason) out->job_reason[j] = unsuccessful[j] ? unsuccessful_reason[j] : (uint8_t)ARMADA_REASON_NONE;
+      if (out->job_seq) out->job_seq[j] = job_seq[j];
     }
     if (out->node_alloc) std::memcpy(out->node_alloc, db.alloc.data(), db.alloc.size() * sizeof(int64_t));
     for (uint32_t q = 0; q < Q; ++q) {
