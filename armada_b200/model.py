@@ -486,6 +486,7 @@ class RoundInputBuilder:
                 if ok:
                     type_match[r, t >> 5] |= np.uint32(1 << (t & 31))
         self.row_specs, self.static_specs, self.type_specs = row_specs, static_specs, type_specs
+        self.type_keys = list(types.keys())
 
         a = self._arr
         self.node_index = a([n.index for n in self.nodes] or [0], np.uint64)

@@ -191,7 +191,18 @@ class Env:
         if "neg" in n:
             return -self.ev(n["neg"])
         if "op" in n:
+            # Go constant expressions are exact (arbitrary precision) and rounded once
+            from fractions import Fraction
             l, r = self.ev(n["l"]), self.ev(n["r"])
+            if isinstance(l, (int, float, Fraction)) and isinstance(r, (int, float, Fraction)):
+                both_int = isinstance(l, int) and isinstance(r, int)
+                fl, fr = Fraction(l), Fraction(r)
+                v = {"+": lambda: fl + fr, "-": lambda: fl - fr, "*": lambda: fl * fr, "/": lambda: fl / fr}[n["op"]]()
+                if both_int and n["op"] != "/":
+                    return int(v)
+                if both_int and v.denominator == 1:
+                    return int(v)  # Go integer constant division of exact multiples
+                return v
             return {"+": lambda: l + r, "-": lambda: l - r, "*": lambda: l * r, "/": lambda: l / r}[n["op"]]()
         if "call" in n:
             name = n["call"]

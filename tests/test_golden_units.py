@@ -1,0 +1,236 @@
+"""Oracle pinned against the reference's unit-level known-answer tables (CPU only):
+  TestNodeTypeIterator / TestNodeTypesIterator  nodedb/nodeiteration_test.go:75-690  (exact visit order)
+  TestCalculateFairShares                       scheduling/context/scheduling_test.go:74-230 (exact doubles)
+  TestDominantResourceFairness                  scheduling/fairness/fairness_test.go:62-170
+  TestGangScheduler                             scheduling/gang_scheduler_test.go:33-760 (single-queue cases)
+  TestNodeIndexKey / bind-evict-unbind vectors  nodedb/encoding_test.go, nodedb/nodedb_test.go:148-422
+"""
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import fixtures as fx
+import go_tables as gt
+import oracle_lib
+from armada_b200 import abi
+from armada_b200.model import (JobSpec, NodeSpec, PriorityClass, QueueSpec, ResourceType, RoundInputBuilder,
+                               SchedulingConfig)
+
+NTI = gt.load_cases("node_type_iterator")
+NTSI = gt.load_cases("node_types_iterator")
+FAIR = gt.load_cases("calculate_fair_shares")
+DRF = gt.load_cases("dominant_resource_fairness")
+GANG = gt.load_cases("gang_scheduler")
+
+
+def _iterator_case(case, multi):
+    env = gt.Env()
+    for name in ("nodeTypeA", "nodeTypeB", "nodeTypeC", "nodeTypeD"):
+        env.ids[name] = name
+        env.calls[name + ".GetId"] = (lambda n: (lambda: n))(name)
+    tc = env.ev(case)
+    cfg = fx.test_scheduling_config()
+    nodes = tc["nodes"]
+    for i, n in enumerate(nodes):  # "Set monotonically increasing node IDs" (test driver)
+        n.id, n.index = str(i), i
+        n.labels[fx.TestHostnameLabel] = n.id
+    synth_jobs = gt.materialize_used(cfg, nodes, env.fx)
+    b = RoundInputBuilder(cfg, nodes, synth_jobs, [QueueSpec("A")])
+    wanted = set(tc["nodeTypeIds"] if multi else [tc["nodeTypeId"]])
+    row = 0
+    b.type_match[row, :] = 0
+    for t, key in enumerate(b.type_keys):
+        if key[0] == "forced" and key[1] in wanted:
+            b.type_match[row, t >> 5] |= np.uint32(1 << (t & 31))
+    f = cfg.factory()
+    rr = f.from_job(dict(tc["resourceRequests"]))
+    ireq = [int(rr[f.index[r.name]]) for r in cfg.indexed_resources]
+    db = oracle_lib.OracleNodeDb(b.input)
+    got = db.iterate(row, int(tc["priority"]), ireq)
+    assert got == [int(x) for x in tc["expected"]]
+
+
+@pytest.mark.parametrize("name", sorted(NTI.keys()))
+def test_node_type_iterator(name):
+    _iterator_case(NTI[name], multi=False)
+
+
+@pytest.mark.parametrize("name", sorted(NTSI.keys()))
+def test_node_types_iterator(name):
+    _iterator_case(NTSI[name], multi=True)
+
+
+@pytest.mark.parametrize("name", sorted(FAIR.keys()))
+def test_calculate_fair_shares(name):
+    env = gt.Env()
+    for nm, v in (("zeroCpu", 0), ("oneCpu", 1), ("fortyCpu", 40), ("oneHundredCpu", 100), ("oneThousandCpu", 1000)):
+        env.ids[nm] = {"cpu": str(v)}
+    tc = env.ev(FAIR[name])
+    cfg = fx.test_scheduling_config(drf_resources=["cpu"])
+    f = cfg.factory()
+    queues = [QueueSpec(qn, priority_factor=1.0, demand=f.from_job(q["Demand"]), constrained_demand=f.from_job(q["Demand"]))
+              for qn, q in tc["queueCtxs"].items()]
+    weights = {qn: float(q["Weight"]) for qn, q in tc["queueCtxs"].items()}
+    total = f.from_node(tc["availableResources"])
+    b = RoundInputBuilder(cfg, [fx.Fixtures().cpu32()], [], queues, total_resources=total)
+    for qn, w in weights.items():  # the test passes weights directly (not 1/priorityFactor)
+        b.qw[b.queue_index[qn]] = w
+    res = oracle_lib.round_schedule(b.input)
+    for qn in weights:
+        qi = b.queue_index[qn]
+        for col, key in enumerate(("expectedFairShares", "expectedDemandCappedAdjustedFairShares", "expectedUncappedAdjustedFairShares")):
+            want = float(tc[key][qn])
+            got = float(res.queue_fair_share[qi, col])
+            assert got == want, f"{key}[{qn}]: {got!r} != {want!r}"  # exact float64 equality, like assert.Equal
+
+
+@pytest.mark.parametrize("name", sorted(DRF.keys()))
+def test_dominant_resource_fairness(name):
+    env = gt.Env()
+    env.ids["rlFactory"] = None
+    env.ids["poolName"] = "pool"
+    env.calls["fooBarBaz"] = lambda _f, a, b_, c: {"foo": a, "bar": b_, "baz": c}
+    tc = env.ev(DRF[name])
+    names = ["foo", "bar", "baz"]
+    scale = Fraction(1, 1000)  # unset resolution ⇒ milli (resolutionToScale)
+    to_i = lambda m: np.array([int(Fraction(str(m[n])) / scale) for n in names], np.int64)  # noqa: E731
+    total, alloc = to_i(tc["totalResources"]), to_i(tc["allocation"])
+    cfgd = tc["config"]
+    mult = {n: 0.0 for n in names}
+    exp = cfgd.get("ExperimentalDominantResourceFairnessResourcesToConsider")
+    pools = cfgd.get("Pools") or []
+    for p in pools:  # pool override (fairness.go:46-52)
+        if p.get("Name") == "pool" and p.get("DominantResourceFairnessResourcesToConsider"):
+            exp = p["DominantResourceFairnessResourcesToConsider"]
+    plain = cfgd.get("DominantResourceFairnessResourcesToConsider") or []
+    if exp and plain and not pools:
+        pytest.skip("invalid config case")
+    if exp and (not plain or pools):
+        for r in exp:
+            nm, m = (r[0], r[1]) if isinstance(r, list) else (r["Name"], r["Multiplier"])
+            mult[nm] = float(m) if float(m) > 0 else 1.0
+    else:
+        for nm in plain:
+            mult[nm] = 1.0
+    m = np.array([mult[n] for n in names], np.float64)
+    lib = oracle_lib.load()
+    cost = lib.armada_oracle_drf_cost(3, total.ctypes.data_as(abi.i64p), m.ctypes.data_as(abi.f64p), alloc.ctypes.data_as(abi.i64p))
+    w = float(tc.get("weight", 1.0)) or 1.0
+    assert cost / w == float(tc["expectedCost"])
+
+
+def _single_queue(gangs):
+    return len({j.queue for g in gangs for j in g}) == 1
+
+
+@pytest.mark.parametrize("name", sorted(GANG.keys()))
+def test_gang_scheduler(name):
+    """TestGangScheduler cases whose gangs all belong to one queue are order-equivalent to a
+    QueueScheduler pass over that queue (gangs in submit order), so they can be driven through the
+    round entry point."""
+    env = gt.Env()
+    env.calls["testfixtures.WithNodeUniformityGangAnnotationsJobs"] = lambda jobs, label: (_ for _ in ()).throw(gt.UnsupportedCase("node uniformity"))
+    try:
+        tc = env.ev(GANG[name])
+    except gt.UnsupportedCase as e:
+        pytest.skip(f"not modelled: {e}")
+    gangs = tc["Gangs"]
+    if not _single_queue(gangs):
+        pytest.skip("multi-queue gang case: direct GangScheduler order differs from queue order")
+    if tc.get("AddAwayQueueContexts"):
+        pytest.skip("away queue contexts")
+    cfg = tc["SchedulingConfig"]
+    nodes = tc["Nodes"]
+    t = 0
+    jobs = []
+    for gi, g in enumerate(gangs):
+        for j in g:
+            t += 1
+            j.submit_time = t
+            if len(g) == 1:
+                j.gang_id, j.gang_cardinality = None, 1
+            jobs.append(j)
+    try:
+        synth = gt.materialize_used(cfg, nodes, env.fx)
+    except gt.UnsupportedCase as e:
+        pytest.skip(str(e))
+    qname = jobs[0].queue
+    b = RoundInputBuilder(cfg, nodes, jobs + synth, [QueueSpec(qname, 1.0)])
+    res = oracle_lib.round_schedule(b.input)
+    got = []
+    for gi, g in enumerate(gangs):
+        st = [int(res.job_state[b.job_pos[j.id]]) for j in g]
+        if all(s == abi.JOB_SCHEDULED for s in st):
+            got.append(gi)
+        else:
+            assert all(s != abi.JOB_SCHEDULED for s in st), "gang partially scheduled"
+    assert got == sorted(tc.get("ExpectedScheduledIndices") or [])
+    cum = tc.get("ExpectedCumulativeScheduledJobs")
+    if cum:
+        assert int(res.out.num_scheduled_jobs) == int(cum[-1])
+
+
+def test_node_index_key_bytes():
+    """TestNodeIndexKey (nodedb/encoding_test.go): layout | typeId | res... | nodeIndex |, big endian,
+    sign bit flipped for int64."""
+    lib = oracle_lib.load()
+    q = np.array([1, -2, 3], np.int64)
+    res = np.array([1, 1, 1], np.int64)
+    out = np.zeros(8 * 5, np.uint8)
+    lib.armada_oracle_node_index_key(3, 7, q.ctypes.data_as(abi.i64p), res.ctypes.data_as(abi.i64p), 9, 1, out.ctypes.data_as(abi.u8p))
+    words = [int.from_bytes(bytes(out[8 * i: 8 * i + 8]), "big") for i in range(5)]
+    assert words[0] == 7 and words[4] == 9
+    assert words[1] == 1 ^ (1 << 63) and words[2] == ((-2) & (2**64 - 1)) ^ (1 << 63) and words[3] == 3 ^ (1 << 63)
+    # rounding (TestRoundQuantityToResolution): toward zero to a multiple of the resolution
+    q = np.array([1999, -1999, 2000], np.int64)
+    res = np.array([1000, 1000, 1000], np.int64)
+    lib.armada_oracle_node_index_key(3, 0, q.ctypes.data_as(abi.i64p), res.ctypes.data_as(abi.i64p), 0, 1, out.ctypes.data_as(abi.u8p))
+    words = [int.from_bytes(bytes(out[8 * i: 8 * i + 8]), "big") ^ (1 << 63) for i in range(1, 4)]
+    signed = [w - 2**64 if w >= 2**63 else w for w in words]
+    assert signed == [1000, -1000, 2000]
+    # byte order == numeric order (TestNodeIndexKeyComparison)
+    keys = []
+    for v in (-5, -1, 0, 1, 7):
+        q = np.array([v, 0, 0], np.int64)
+        lib.armada_oracle_node_index_key(3, 1, q.ctypes.data_as(abi.i64p), np.ones(3, np.int64).ctypes.data_as(abi.i64p), 0, 0, out.ctypes.data_as(abi.u8p))
+        keys.append(bytes(out))
+    assert keys == sorted(keys)
+
+
+def test_eviction_allocatable_vectors():
+    """TestEviction (nodedb/nodedb_test.go:363-422): a PriorityClass0 job and a non-preemptible
+    PriorityClass3 job (1 cpu / 4Gi each) on a 32 cpu / 256Gi node, then both evicted."""
+    F = fx.Fixtures()
+    cfg = fx.test_scheduling_config()
+    node = F.cpu32()
+    j0 = F.job("A", fx.PriorityClass0, {"cpu": "1", "memory": "4Gi"})
+    j3 = F.job("A", fx.PriorityClass3, {"cpu": "1", "memory": "4Gi"})
+    for j in (j0, j3):
+        j.node = node.id
+    b = RoundInputBuilder(cfg, [node], [j0, j3], [QueueSpec("A")])
+    db = oracle_lib.OracleNodeDb(b.input)
+    f = cfg.factory()
+    prios = b.priorities  # [-1,0,1,2,3,28000,29000,30000]
+    cpu, mem = f.index["cpu"], f.index["memory"]
+
+    def vec(c, m):
+        v = np.zeros(f.D, np.int64)
+        v[cpu], v[mem] = c * 1000, m * 2**30
+        return v
+
+    a = db.get_alloc(0)
+    for lvl, p in enumerate(prios):
+        want = vec(30, 248) if p <= 0 else vec(31, 252)  # non-preemptible job deducted at every level
+        assert (a[lvl] == want).all(), (p, a[lvl], want)
+    db.evict(0)
+    db.evict(1)
+    a = db.get_alloc(0)
+    for lvl, p in enumerate(prios):
+        want = vec(30, 248) if p == -1 else vec(32, 256)  # evicted jobs only count at EvictedPriority
+        assert (a[lvl] == want).all(), (p, a[lvl], want)
+    db.unbind(0)
+    db.unbind(1)
+    a = db.get_alloc(0)
+    assert all((a[lvl] == vec(32, 256)).all() for lvl in range(len(prios)))
