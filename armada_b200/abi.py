@@ -176,14 +176,8 @@ class ArmadaError(RuntimeError):
         self.status = status
 
 
-def load_product() -> C.CDLL:
-    """Load libarmada_b200.so (the CUDA product).  Fails loudly: there is no CPU fallback."""
-    global _product
-    if _product is not None:
-        return _product
-    if not os.path.exists(PRODUCT_LIB_PATH):
-        raise ArmadaError(E_NO_DEVICE, f"{PRODUCT_LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = C.CDLL(PRODUCT_LIB_PATH)
+def declare_prototypes(lib: C.CDLL) -> None:
+    """argtypes/restype of every entry point of include/armada_b200.h."""
     vp = C.c_void_p
     lib.armada_round_create.argtypes = [C.c_int32, C.POINTER(vp)]
     lib.armada_round_create.restype = C.c_int32
@@ -203,6 +197,17 @@ def load_product() -> C.CDLL:
     lib.armada_last_error.restype = C.c_char_p
     lib.armada_abi_version.argtypes = []
     lib.armada_abi_version.restype = C.c_uint32
+
+
+def load_product() -> C.CDLL:
+    """Load libarmada_b200.so (the CUDA product).  Fails loudly: there is no CPU fallback."""
+    global _product
+    if _product is not None:
+        return _product
+    if not os.path.exists(PRODUCT_LIB_PATH):
+        raise ArmadaError(E_NO_DEVICE, f"{PRODUCT_LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(PRODUCT_LIB_PATH)
+    declare_prototypes(lib)
     _product = lib
     return lib
 

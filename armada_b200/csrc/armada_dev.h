@@ -10,16 +10,20 @@
 //   jobs       SoA over J         class / queue / gang / order rank / run binding
 //   per-job round state           bound node, evicted flag, scheduled-at priority, qctx set
 //                                 membership, pod scheduling result
-// The persistent round kernel keeps per-queue DRF state and the best-fit tournament trees
-// in shared memory (see armada_round.cu).
+//   g0         [N]     u64        nodes sorted by their packed level-0 best-fit key (rebuilt before
+//                                 every schedule pass that has queued jobs)
+// The persistent round kernel keeps per-queue DRF state and the heads of the best-fit index
+// (32-entry sorted windows per job class) in shared memory (see armada_pass.inc).
 #pragma once
 #include <stdint.h>
+#ifndef ARMADA_EMU
 #include <vector_types.h>
+#endif
 
 #include "armada_b200.h"
 
 #define ARMADA_DEV_MAX_QUEUES 128
-#define ARMADA_DEV_MAX_SLOTS 32
+#define ARMADA_DEV_MAX_SLOTS 60  // best-fit index slots (4 per index warp)
 #define ARMADA_DEV_VARIANTS (1 + ARMADA_MAX_AWAY)  // home + away node types per class
 
 struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
@@ -29,6 +33,7 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int64_t res_scale[ARMADA_MAX_RESOURCES];  // per FACTORY resource: index resolution or 1
   int32_t key_shift[ARMADA_MAX_RESOURCES];  // per indexed resource i: bit position in the packed key
   int32_t node_bits;                        // low bits of the key hold the node (id-rank) index
+  int32_t key_total_bits;                   // bits used by the packed key (< 64)
   int32_t priorities[ARMADA_MAX_PRIORITIES];
   ArmadaPriorityClass pcs[ARMADA_MAX_PRIORITY_CLASSES];
   int64_t total_resources[ARMADA_MAX_RESOURCES];
@@ -40,12 +45,11 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   uint32_t max_lookback, disallowed_mask;
   double global_tokens;
   int64_t global_burst;
-  int32_t tile_shift;  // leaf tile = 1 << tile_shift nodes
-  int32_t num_tiles, num_groups, num_slots, sw, tw;
+  int32_t max_slots, sw, tw;
   // shared-memory layout of k_schedule_pass (byte offsets from the dynamic smem base)
   int32_t win_w;       // stream-window records per queue (power of two, <= 32)
-  int32_t nc_entries;  // node-cache entries (power of two)
-  uint32_t off_cls, off_win, off_nc_tag, off_nc_val, off_root, off_l2, off_leaf;
+  uint32_t off_cls, off_win, off_touched, off_slot, off_skey, off_srow, off_ssc, off_sgpos, off_hb_key, off_hb_row, off_hb_sc,
+      off_ring;
 };
 
 struct DevPtrs {
@@ -121,8 +125,8 @@ struct DevPtrs {
   uint32_t* sort_vals2;            // [J]
   uint32_t* counters;              // [16] misc device counters (evicted count, …)
   uint8_t* unfeasible;             // [C] UnfeasibleSchedulingKeys: reason or 0
-  int16_t* slot_of;                // [C*VARIANTS*PL] tree slot, -1 none yet, -2 uncached
-  uint32_t* slot_static;           // [slots][ceil(N/32)] static-ok bitmap per slot
+  unsigned long long* g0;          // [N] nodes sorted by packed level-0 key (best-fit order)
+  unsigned long long* g0_tmp;      // [N] radix-sort ping-pong buffer
   uint32_t* undo_log;              // [5 * J] txn undo records
   // fair preemption scratch
   int64_t* fp_avail;               // [D][N]

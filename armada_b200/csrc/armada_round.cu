@@ -21,7 +21,15 @@
 //     resident node SoA with redux.sync arg-min on a packed 64-bit (resources…, node-id) key.
 //     A probe is a root read; a bind re-scans one tile per affected tree.
 //   Tensor cores are not used: this is integer compare/select work.
+#ifdef ARMADA_EMU
+#include "cuda_emu.h"  // tools/simt_emu: deterministic CPU SIMT emulator (dev/test tooling only)
+#else
 #include <cuda_runtime.h>
+#define ARMADA_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define ARMADA_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define ARMADA_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(count) : "memory")
+static __device__ __forceinline__ void armada_emu_yield() {}
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -422,6 +430,22 @@ __global__ void k_rs_scatter(const unsigned long long* keys, const uint32_t* val
       ++cnt;
     }
   }
+}
+
+// Packed level-0 key of every node (the input of the G0 sort).  A node with a negative row can
+// fit nothing until it changes (and then it is "touched"): it sorts last.
+__global__ void k_g0_keys(DevCfg c, DevPtrs P) {
+  size_t n = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (n >= c.N) return;
+  unsigned long long key = n;
+  bool neg = false;
+  for (int i = 0; i < c.R; ++i) {
+    int64_t v = P.alloc[(size_t)c.indexed_resource[i] * c.N + n];
+    neg = neg || v < 0;
+    key |= (unsigned long long)v << c.key_shift[i];
+  }
+  unsigned long long marker = 1ull << c.key_total_bits;
+  P.g0[n] = neg ? (marker | n) : key;
 }
 
 // evq_start[q] = first position in the sorted evicted list whose queue is >= q.

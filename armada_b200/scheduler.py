@@ -19,8 +19,10 @@ class DeviceRound:
     """Owns one `ArmadaRound*` (device context).  upload → run → download, like
     populateNodeDb → Schedule → result read-back in scheduling_algo.go:740-840."""
 
-    def __init__(self, device: int = 0):
-        self.lib = abi.load_product()
+    def __init__(self, device: int = 0, lib=None):
+        # `lib` is for tests only (tests/emu_lib.py steps the same kernel source through a CPU SIMT
+        # emulator); the product always loads the CUDA library and fails loudly without it.
+        self.lib = lib if lib is not None else abi.load_product()
         self.h = C.c_void_p()
         self._check(self.lib.armada_round_create(device, C.byref(self.h)))
         self._input: Optional[abi.RoundInput] = None

@@ -1,0 +1,105 @@
+"""Kernel-logic parity WITHOUT a GPU: the same CUDA source (armada_b200/csrc/*.cu|inc) compiled
+by g++ against tools/simt_emu/cuda_emu.h (deterministic SIMT emulator, test tooling only) and
+compared bit-for-bit with the CPU oracle.  The real parity tests are tests/test_parity_gpu.py
+(pytest -m gpu, through the nvcc-built product library); this module exists so that control-flow /
+data-structure bugs in the kernels are caught on a CPU-only box.  EMU_ORDER=reverse runs the
+lanes of every warp in the opposite order (catches missing __syncwarp in either direction)."""
+import os
+
+import pytest
+
+import emu_lib
+import go_tables as gt
+import oracle_lib
+from armada_b200 import abi, synth
+
+_dev = None
+
+
+def emu_round(inp):
+    global _dev
+    if _dev is None:
+        _dev = emu_lib.emu_round()
+    return _dev.schedule(inp)
+
+
+def assert_parity(inp, label=""):
+    want = oracle_lib.round_schedule(inp)
+    got = emu_round(inp)
+    bad = got.diff(want)
+    assert not bad, f"{label}: emulated kernel != oracle:\n  " + "\n  ".join(bad)
+    return got, want
+
+
+@pytest.fixture(params=["forward", "reverse"])
+def lane_order(request):
+    old = os.environ.get("EMU_ORDER")
+    os.environ["EMU_ORDER"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("EMU_ORDER", None)
+    else:
+        os.environ["EMU_ORDER"] = old
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_rounds(seed, lane_order):
+    r = synth.random_round(
+        seed,
+        away=(seed % 4 == 1),
+        round_limit=(seed % 6 == 3),
+        queue_limits=(seed % 6 == 4),
+        protected_fraction=0.5 if seed % 3 == 2 else 0.0,
+        lookback=40 if seed % 5 == 1 else 0,
+        n_nodes=40 + 13 * (seed % 7),
+        n_jobs=300 + 50 * (seed % 5),
+        n_running=80 + 20 * (seed % 4),
+    )
+    assert_parity(r.to_input(), r.name)
+
+
+@pytest.mark.parametrize("seed", [100, 101])
+def test_random_rounds_many_nodes(seed):
+    r = synth.random_round(seed, n_nodes=1500 + 700 * (seed % 3), n_queues=9, n_jobs=2500, n_running=1200,
+                           protected_fraction=0.5 if seed % 2 else 0.0)
+    assert_parity(r.to_input(), r.name)
+
+
+@pytest.mark.parametrize("name,scale", [("C2", 0.02), ("C3", 0.004), ("C4", 0.006), ("C5", 0.004)])
+def test_scaled_configs(name, scale):
+    r = synth.scaled(name, scale)
+    got, want = assert_parity(r.to_input(), f"{name}@{scale}")
+    assert got.out.num_result_scheduled == want.out.num_result_scheduled
+
+
+PQS = gt.load_cases("preempting_queue_scheduler")
+QS = gt.load_cases("queue_scheduler")
+
+
+def _emu_round_or_skip(inp):
+    try:
+        got = emu_round(inp)
+    except abi.ArmadaError as e:
+        if e.status == abi.E_UNSUPPORTED:
+            raise gt.UnsupportedCase(str(e))
+        raise
+    want = oracle_lib.round_schedule(inp)
+    bad = got.diff(want)
+    assert not bad, "emulated kernel != oracle:\n  " + "\n  ".join(bad)
+    return got
+
+
+@pytest.mark.parametrize("name", sorted(PQS.keys()))
+def test_reference_pqs_tables(name):
+    try:
+        gt.run_pqs_case(PQS[name], _emu_round_or_skip)
+    except gt.UnsupportedCase as e:
+        pytest.skip(f"outside device domain / not modelled: {e}")
+
+
+@pytest.mark.parametrize("name", sorted(QS.keys()))
+def test_reference_queue_scheduler_tables(name):
+    try:
+        gt.run_queue_scheduler_case(QS[name], _emu_round_or_skip)
+    except gt.UnsupportedCase as e:
+        pytest.skip(f"outside device domain / not modelled: {e}")
