@@ -29,6 +29,7 @@
 #define ARMADA_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define ARMADA_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(count) : "memory")
 static __device__ __forceinline__ void armada_emu_yield() {}
+#define ARMADA_NOINLINE __noinline__
 #endif
 
 #include <algorithm>

@@ -302,7 +302,7 @@ def main():
             "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args.workload, inp, world),
             "placements_per_round": int(placements / args.steps),
             "control_warp_cycles_per_iteration": {n: round(int(stats.phase_cycles[i]) / max(1, int(stats.loop_iterations)), 1) for i, n in enumerate(
-                ("queue_argmin", "gang_total", "node_select", "node_row_update", "tree_refresh_wait", "result_algebra", "iterator_advance", "clear_total"))},
+                ("queue_argmin", "gang_total", "node_select", "node_row_update", "unused", "result_algebra", "iterator_advance", "clear_total"))},
             "loop_iterations_per_round": int(stats.loop_iterations),
             "gpu_launches": int(cnt[3]),
             "clocks": clocks,
@@ -313,7 +313,7 @@ def main():
                          "algorithmic_bytes_per_probe": probe_bytes, "probes_per_launch": int(local_probes / args.steps),
                          "kernel_ms_per_launch": pass_ms / args.steps,
                          "kernel_share_of_step": pass_ms / dev_ms if dev_ms else None,
-                         "note": "smarter-than-scan (tournament trees): >1.0 means faster than re-scanning every node per probe"},
+                         "note": "smarter-than-scan (sorted index + per-class windows): frac > 1.0 means faster than re-scanning every node per probe"},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)

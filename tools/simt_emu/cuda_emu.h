@@ -30,8 +30,10 @@
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define ARMADA_NOINLINE __attribute__((noinline))
 #define __align__(n) alignas(n)
 #define __shared__ static
+#define __constant__ static
 #define __restrict__
 
 struct uint4 {
@@ -501,6 +503,11 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
 }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) {
   *v = attr == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 0;
+  return cudaSuccess;
+}
+template <class T>
+static inline cudaError_t cudaMemcpyToSymbolAsync(T& sym, const void* src, size_t n, size_t off, int, cudaStream_t) {
+  memcpy((char*)&sym + off, src, n);
   return cudaSuccess;
 }
 template <class F>
