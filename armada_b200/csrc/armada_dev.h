@@ -23,7 +23,7 @@
 #include "armada_b200.h"
 
 #define ARMADA_DEV_MAX_QUEUES 128
-#define ARMADA_DEV_MAX_SLOTS 60  // best-fit index slots (4 per index warp)
+#define ARMADA_DEV_MAX_SLOTS 24  // best-fit index slots (2 per index warp)
 #define ARMADA_DEV_VARIANTS (1 + ARMADA_MAX_AWAY)  // home + away node types per class
 
 struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
@@ -49,7 +49,8 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   // shared-memory layout of k_schedule_pass (byte offsets from the dynamic smem base)
   int32_t win_w;       // stream-window records per queue (power of two, <= 32)
   uint32_t off_cls, off_win, off_touched, off_slot, off_skey, off_srow, off_ssc, off_sgpos, off_hb_key, off_hb_row, off_hb_sc,
-      off_ring;
+      off_ring, off_bt_k0, off_bt_k1;
+  int32_t bt_wq;  // batch mode: items per queue per batch (0 = batch mode off)
 };
 
 struct DevPtrs {
@@ -127,6 +128,12 @@ struct DevPtrs {
   uint8_t* unfeasible;             // [C] UnfeasibleSchedulingKeys: reason or 0
   unsigned long long* g0;          // [N] nodes sorted by packed level-0 key (best-fit order)
   unsigned long long* g0_tmp;      // [N] radix-sort ping-pong buffer
+  // batch mode scratch, [Q * bt_wq] each
+  uint32_t* bt_job;
+  uint32_t* bt_cls;
+  uint32_t* bt_pos;                // stream position of the item
+  uint32_t* bt_rank;               // merged position
+  uint2* bt_seq;                   // merged sequence: {job, class}
   uint32_t* undo_log;              // [5 * J] txn undo records
   // fair preemption scratch
   int64_t* fp_avail;               // [D][N]

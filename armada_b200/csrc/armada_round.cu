@@ -30,6 +30,7 @@
 #define ARMADA_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(count) : "memory")
 static __device__ __forceinline__ void armada_emu_yield() {}
 #define ARMADA_NOINLINE __noinline__
+#define ARMADA_EMU_MARK(id) ((void)0)
 #endif
 
 #include <algorithm>

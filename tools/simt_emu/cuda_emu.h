@@ -40,6 +40,10 @@ struct uint4 {
   unsigned x, y, z, w;
 };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+struct uint2 {
+  unsigned x, y;
+};
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct uint3 {
   unsigned x, y, z;
 };
@@ -89,6 +93,7 @@ enum State { RUNNABLE, WAIT_WARP, WAIT_BAR, DONE };
 
 struct Warp {
   uint64_t vals[2][32];
+  void* site[2][32];  // call site of each lane's collective (divergence check)
   int count[2] = {0, 0};
   uint64_t done = 0;  // completed generations
   int nlanes = 32;
@@ -106,6 +111,7 @@ struct Thread {
   uint64_t gen = 0;       // next warp-collective generation of this lane
   uint64_t wait_gen = 0;  // generation waited for (warp or barrier)
   int wait_bar = 0;
+  int mark = 0;  // last ARMADA_EMU_MARK() passed (debug aid for the watchdog)
   char* stack = nullptr;
 };
 
@@ -173,7 +179,21 @@ inline void run_block() {
     th.sp = (void*)sp;
   }
   unsigned live = B;
+  unsigned long long rounds = 0;
+  const auto t_start = std::chrono::steady_clock::now();
+  const double limit_s = getenv("EMU_LAUNCH_TIMEOUT") ? atof(getenv("EMU_LAUNCH_TIMEOUT")) : 120.0;
   while (live) {
+    if ((++rounds & 0xFFFF) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > limit_s) {
+      fprintf(stderr, "simt_emu: kernel launch exceeded %.0f s (livelock?) in block %u; thread states:\n", limit_s, m.block_idx.x);
+      for (unsigned t = 0; t < B; t += 32) {
+        fprintf(stderr, "  warp %u done=%llu lanes(state:gen):", t / 32, (unsigned long long)m.threads[t].warp->done);
+        for (unsigned i = t; i < t + 32 && i < B; ++i) fprintf(stderr, " %d:%llu@%d", (int)m.threads[i].state, (unsigned long long)m.threads[i].gen, m.threads[i].mark);
+        fprintf(stderr, "\n    pending collective sites:");
+        for (int i = 0; i < 32; ++i) fprintf(stderr, " %p", m.threads[t].warp->site[m.threads[t].warp->done & 1][i]);
+        fprintf(stderr, "\n");
+      }
+      abort();
+    }
     bool progressed = false;
     for (unsigned tt = 0; tt < B; ++tt) {
       // EMU_ORDER=reverse runs the lanes of every warp from 31 down to 0: code that is only correct
@@ -241,13 +261,14 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F&& f) {
 }
 
 // ---- warp collectives (all lanes of the warp participate) ---------------------------------------
-inline const uint64_t* collect(uint64_t v) {
+__attribute__((noinline)) inline const uint64_t* collect(uint64_t v) {
   Machine& m = M();
   Thread* t = m.cur;
   Warp* W = t->warp;
   uint64_t g = t->gen++;
   int b = (int)(g & 1);
   W->vals[b][t->lane] = v;
+  W->site[b][t->lane] = __builtin_return_address(0);
   if (++W->count[b] == W->nlanes) {
     W->count[b] = 0;
     W->done = g + 1;
@@ -517,5 +538,6 @@ static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess
   if (getenv("EMU_TRACE")) fprintf(stderr, "emu launch %s\n", #kern); \
   emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); }); \
   emu_check_canaries(#kern)
+#define ARMADA_EMU_MARK(id) (emu::M().cur->mark = (id))
 #define ARMADA_DYN_SMEM(name) unsigned char* name = emu::M().dyn_smem
 #define ARMADA_NAMED_BARRIER(id, count) emu::barrier((id), (count))
