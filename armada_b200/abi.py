@@ -161,6 +161,7 @@ class RoundStats(C.Structure):
         ("device_ms", C.c_double),
         ("schedule_pass_ms", C.c_double),
         ("phase_cycles", C.c_uint64 * 8),
+        ("batch_cycles", C.c_uint64 * 8),
     ]
 
 

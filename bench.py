@@ -302,8 +302,11 @@ def main():
             "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args.workload, inp, world),
             "placements_per_round": int(placements / args.steps),
             "control_warp_cycles_per_iteration": {n: round(int(stats.phase_cycles[i]) / max(1, int(stats.loop_iterations)), 1) for i, n in enumerate(
-                ("queue_argmin", "gang_total", "node_select", "node_row_update", "unused", "result_algebra", "iterator_advance", "clear_total"))},
+                ("queue_argmin", "gang_total", "node_select", "node_row_update", "batched_iterations", "result_algebra", "iterator_advance", "clear_total"))},
             "loop_iterations_per_round": int(stats.loop_iterations),
+            "batch_mode": {"iterations": int(stats.phase_cycles[4]), "batches": int(stats.batch_cycles[6]),
+                           "cycles_per_batched_iteration": {n: round(int(stats.batch_cycles[i]) / max(1, int(stats.phase_cycles[4])), 1) for i, n in enumerate(
+                               ("item_build", "horizon", "merge_rank", "node_assign", "commit_repeek", "control"))}},
             "gpu_launches": int(cnt[3]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

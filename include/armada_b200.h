@@ -247,8 +247,12 @@ typedef struct {
                                     kernel launches (the dominant kernel) inside device_ms    */
   uint64_t phase_cycles[8];      /* device only: SM clock cycles the control warp spent in
                                     0 queue arg-min, 1 gang bookkeeping+constraints, 2 node
-                                    selection, 3 node row update, 4 tree refresh wait,
+                                    selection, 3 node row update, 4 (see batch_cycles),
                                     5 result algebra, 6 iterator advance, 7 cost update       */
+  uint64_t batch_cycles[8];      /* device only: batch mode (many loop iterations at once): SM
+                                    cycles in 0 item build, 1 horizon, 2 merge ranks, 3 node
+                                    assignment, 4 commit, 5 re-peek; 6 = number of batches,
+                                    7 unused.  phase_cycles[4] = iterations run in batch mode */
 } ArmadaRoundStats;
 
 /* ---- product entry points (libarmada_b200.so) ------------------------------------- */
