@@ -23,7 +23,7 @@
 #include "armada_b200.h"
 
 #define ARMADA_DEV_MAX_QUEUES 128
-#define ARMADA_DEV_MAX_SLOTS 24  // best-fit index slots (2 per index warp)
+#define ARMADA_DEV_MAX_SLOTS 22  // best-fit index slots: 2 per owning index warp (11 owners; batch mode keeps both in registers)
 #define ARMADA_DEV_VARIANTS (1 + ARMADA_MAX_AWAY)  // home + away node types per class
 
 struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
