@@ -162,6 +162,7 @@ class RoundStats(C.Structure):
         ("schedule_pass_ms", C.c_double),
         ("phase_cycles", C.c_uint64 * 8),
         ("batch_cycles", C.c_uint64 * 8),
+        ("batch_debug", C.c_uint64 * 8),
     ]
 
 

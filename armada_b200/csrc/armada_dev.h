@@ -32,6 +32,7 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int32_t indexed_resource[ARMADA_MAX_RESOURCES];
   int64_t res_scale[ARMADA_MAX_RESOURCES];  // per FACTORY resource: index resolution or 1
   int32_t key_shift[ARMADA_MAX_RESOURCES];  // per indexed resource i: bit position in the packed key
+  int32_t res_key_shift[ARMADA_MAX_RESOURCES];  // per FACTORY resource d: bit position, or -1 if not indexed
   int32_t node_bits;                        // low bits of the key hold the node (id-rank) index
   int32_t key_total_bits;                   // bits used by the packed key (< 64)
   int32_t priorities[ARMADA_MAX_PRIORITIES];
@@ -150,5 +151,6 @@ struct DevPtrs {
   int64_t* s_evicted;              // [D]
   int64_t* s_counts;               // [8]: 0 numScheduledJobs 1 numScheduledGangs 2 numEvictedJobs
                                    //      3 termination(pass1) 4 global tokens (double bits)
+  uint32_t* dbg_host;              // [64] host-mapped: written by the device watchdog before it traps
   unsigned long long* stats;       // [8]: loop iters, probes, placements, fair scans, rescans
 };

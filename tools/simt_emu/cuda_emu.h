@@ -483,6 +483,19 @@ static inline cudaError_t cudaFree(void* p) {
   free(p);
   return cudaSuccess;
 }
+enum { cudaHostAllocMapped = 2 };
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, int) {
+  *p = malloc(n);
+  return *p ? cudaSuccess : 2;
+}
+static inline cudaError_t cudaFreeHost(void* p) {
+  free(p);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, int) {
+  *d = h;
+  return cudaSuccess;
+}
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) {
   memcpy(d, s, n);
   return cudaSuccess;
