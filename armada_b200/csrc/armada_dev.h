@@ -135,6 +135,7 @@ struct DevPtrs {
   uint32_t* bt_pos;                // stream position of the item
   uint32_t* bt_rank;               // merged position
   uint2* bt_seq;                   // merged sequence: {job, class}
+  uint32_t* bt_node;               // node of every placement of the batch, in merged order
   uint32_t* undo_log;              // [5 * J] txn undo records
   // fair preemption scratch
   int64_t* fp_avail;               // [D][N]
