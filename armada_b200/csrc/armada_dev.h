@@ -50,8 +50,9 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   // shared-memory layout of k_schedule_pass (byte offsets from the dynamic smem base)
   int32_t win_w;       // stream-window records per queue (power of two, <= 32)
   uint32_t off_cls, off_win, off_touched, off_slot, off_skey, off_srow, off_ssc, off_sgpos, off_hb_key, off_hb_row, off_hb_sc,
-      off_ring, off_bt_k0, off_bt_k1;
+      off_ring, off_bt_k0, off_bt_k1, off_bt_id;
   int32_t bt_wq;  // batch mode: items per queue per batch (0 = batch mode off)
+  int32_t bt_np;  // Q * bt_wq rounded up to a power of two (sort size)
 };
 
 struct DevPtrs {
