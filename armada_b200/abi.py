@@ -199,6 +199,8 @@ def declare_prototypes(lib: C.CDLL) -> None:
     lib.armada_last_error.restype = C.c_char_p
     lib.armada_abi_version.argtypes = []
     lib.armada_abi_version.restype = C.c_uint32
+    lib.armada_abi_sizeof.argtypes = [C.c_uint32]
+    lib.armada_abi_sizeof.restype = C.c_uint32
 
 
 def load_product() -> C.CDLL:
@@ -224,4 +226,5 @@ PRODUCT_SYMBOLS = [
     "armada_strerror",
     "armada_last_error",
     "armada_abi_version",
+    "armada_abi_sizeof",
 ]

@@ -278,6 +278,9 @@ int32_t armada_round_schedule(ArmadaRound* r, const ArmadaRoundInput* in, Armada
 const char* armada_strerror(int32_t status);
 const char* armada_last_error(void);
 uint32_t armada_abi_version(void);
+/* sizeof() of the three boundary structs as compiled into the library (0 input, 1 output,
+ * 2 stats); bindings check them against their own mirror of this header. */
+uint32_t armada_abi_sizeof(uint32_t which);
 
 #ifdef __cplusplus
 }

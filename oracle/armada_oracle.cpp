@@ -1750,4 +1750,13 @@ int32_t armada_oracle_node_index_key(uint32_t r, uint64_t node_type_id, const in
   return ARMADA_OK;
 }
 
+uint32_t armada_oracle_abi_sizeof(uint32_t which) {
+  switch (which) {
+    case 0: return (uint32_t)sizeof(ArmadaRoundInput);
+    case 1: return (uint32_t)sizeof(ArmadaRoundOutput);
+    case 2: return (uint32_t)sizeof(ArmadaRoundStats);
+    default: return 0;
+  }
+}
+
 }  // extern "C"

@@ -63,6 +63,9 @@ int32_t armada_oracle_node_index_key(uint32_t r, uint64_t node_type_id, const in
                                      const int64_t* resolution, uint64_t node_index, int rounded,
                                      uint8_t* out);
 
+/* sizeof() of ArmadaRoundInput / Output / Stats as compiled into the oracle (0, 1, 2). */
+uint32_t armada_oracle_abi_sizeof(uint32_t which);
+
 #ifdef __cplusplus
 }
 #endif
