@@ -34,6 +34,9 @@ static __device__ __forceinline__ void armada_emu_yield() {}
 #endif
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>

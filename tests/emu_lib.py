@@ -26,7 +26,7 @@ def build(force: bool = False) -> None:
         subprocess.run(
             ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DARMADA_EMU", "-x", "c++",
              os.path.join(CSRC, "armada_round.cu"), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", EMU_DIR,
-             "-o", EMU_LIB], check=True)
+             "-o", EMU_LIB, "-lpthread"], check=True)
 
 
 def load() -> C.CDLL:
