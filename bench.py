@@ -306,9 +306,7 @@ def main():
             "loop_iterations_per_round": int(stats.loop_iterations),
             "batch_mode": {"iterations": int(stats.phase_cycles[4]), "batches": int(stats.batch_cycles[6]),
                            "cycles_per_batched_iteration": {n: round(int(stats.batch_cycles[i]) / max(1, int(stats.phase_cycles[4])), 1) for i, n in enumerate(
-                               ("item_build", "horizon", "merge_rank", "node_assign", "commit_repeek", "control"))},
-                           "index_warp0": {n: int(stats.batch_debug[i]) for i, n in enumerate(
-                               ("writer_wait_cycles", "writer_work_cycles", "owner_ringspace_wait_cycles", "nonowner_flag_wait_cycles", "unused", "owned_items_warp0", "unused2"))}},
+                               ("item_build", "horizon", "merge_rank", "node_assign", "commit_repeek", "control"))}},
             "gpu_launches": int(cnt[3]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

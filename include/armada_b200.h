@@ -253,9 +253,7 @@ typedef struct {
                                     cycles in 0 item build, 1 horizon, 2 merge ranks, 3 node
                                     assignment, 4 commit, 5 re-peek; 6 = number of batches,
                                     7 unused.  phase_cycles[4] = iterations run in batch mode */
-  uint64_t batch_debug[8];       /* device only: index warp 0 during node assignment: cycles waiting
-                                    for another owner / acting as owner / window updates / refills;
-                                    counts of refills, owned items, items */
+  uint64_t batch_debug[8];       /* device only: spare debug counters */
 } ArmadaRoundStats;
 
 /* ---- product entry points (libarmada_b200.so) ------------------------------------- */
