@@ -65,6 +65,15 @@ def test_random_rounds_many_nodes(seed):
     assert_parity(r.to_input(), r.name)
 
 
+@pytest.mark.parametrize("n_queues", [40, 100, 128])
+def test_many_queues(n_queues):
+    """More queues than fit 64 batch items each (the batch windows shrink to 32 / the merge sort to
+    a different power of two); priorities off so that most of the round runs in batch mode."""
+    r = synth.random_round(300 + n_queues, n_nodes=300, n_queues=n_queues, n_jobs=2500, n_running=0, gangs=False, priorities=False)
+    got, _ = assert_parity(r.to_input(), r.name)
+    assert int(got.stats.phase_cycles[4]) > 0
+
+
 @pytest.mark.parametrize("name,scale", [("C2", 0.02), ("C3", 0.004), ("C4", 0.006), ("C5", 0.004)])
 def test_scaled_configs(name, scale):
     r = synth.scaled(name, scale)
