@@ -35,6 +35,9 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int32_t res_key_shift[ARMADA_MAX_RESOURCES];  // per FACTORY resource d: bit position, or -1 if not indexed
   int32_t node_bits;                        // low bits of the key hold the node (id-rank) index
   int32_t key_total_bits;                   // bits used by the packed key (< 64)
+  int32_t key_width[ARMADA_MAX_RESOURCES];  // per indexed resource i: field width in bits
+  unsigned long long key_guard;             // one always-zero bit above every field (0 = no guard bits)
+  int32_t swar_ok;                          // guard bits present and every resource is indexed
   int32_t priorities[ARMADA_MAX_PRIORITIES];
   ArmadaPriorityClass pcs[ARMADA_MAX_PRIORITY_CLASSES];
   int64_t total_resources[ARMADA_MAX_RESOURCES];
