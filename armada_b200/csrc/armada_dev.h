@@ -33,6 +33,7 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int64_t res_scale[ARMADA_MAX_RESOURCES];  // per FACTORY resource: index resolution or 1
   int32_t key_shift[ARMADA_MAX_RESOURCES];  // per indexed resource i: bit position in the packed key
   int32_t res_key_shift[ARMADA_MAX_RESOURCES];  // per FACTORY resource d: bit position, or -1 if not indexed
+  int32_t res_key_width[ARMADA_MAX_RESOURCES];  // per FACTORY resource d: field width (0 if not indexed)
   int32_t node_bits;                        // low bits of the key hold the node (id-rank) index
   int32_t key_total_bits;                   // bits used by the packed key (< 64)
   int32_t key_width[ARMADA_MAX_RESOURCES];  // per indexed resource i: field width in bits
@@ -133,6 +134,7 @@ struct DevPtrs {
   uint8_t* unfeasible;             // [C] UnfeasibleSchedulingKeys: reason or 0
   unsigned long long* g0;          // [N] nodes sorted by packed level-0 key (best-fit order)
   unsigned long long* g0_tmp;      // [N] radix-sort ping-pong buffer
+  uint32_t* g0_sc;                 // [N] static class of the node at every G0 position (aliases g0_tmp after the sort)
   // batch mode scratch, [Q * bt_wq] each
   uint32_t* bt_job;
   uint32_t* bt_cls;

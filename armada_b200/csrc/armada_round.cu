@@ -31,6 +31,7 @@
 static __device__ __forceinline__ void armada_emu_yield() {}
 #define ARMADA_NOINLINE __noinline__
 #define ARMADA_EMU_MARK(id) ((void)0)
+#define ARMADA_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #endif
 
 #include <algorithm>
@@ -451,6 +452,13 @@ __global__ void k_g0_keys(DevCfg c, DevPtrs P) {
   }
   unsigned long long marker = 1ull << c.key_total_bits;
   P.g0[n] = neg ? (marker | n) : key;
+}
+
+// static class of the node at every G0 position
+__global__ void k_g0_sc(DevCfg c, DevPtrs P) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= c.N) return;
+  P.g0_sc[i] = P.node_sclass[(uint32_t)(P.g0[i] & ((1ull << c.node_bits) - 1ull))];
 }
 
 // evq_start[q] = first position in the sorted evicted list whose queue is >= q.

@@ -21,8 +21,9 @@ with DeviceRound(0, lib=lib) as dev:
     d = list(st.batch_debug)
     c = list(st.batch_cycles)
     print("placements", st.placements, "batch_cycles", c)
-    print("debug", d)
+    print("debug", d, "iters", st.loop_iterations, "probes", st.probes, "rescans", st.tree_rescans, "pass_ms", st.schedule_pass_ms, "phase", list(st.phase_cycles))
     if d[0]: print("per touched placement:", [round(x / d[0], 1) for x in d[1:5]])
     print("fresh placements", d[0], "cycles/fresh", d[1] / max(d[0], 1))
     print("candidate lookups", d[3], "cycles/lookup", d[2] / max(d[3], 1), "cursor chunks", d[6])
+    print("cycles per cursor chunk", d[7] / max(d[6], 1))
     print("table gc", d[5], "assign loop cycles", d[4])

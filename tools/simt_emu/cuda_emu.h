@@ -31,6 +31,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define ARMADA_NOINLINE __attribute__((noinline))
+#define ARMADA_PREFETCH_L1(p) ((void)(p))
 #define __align__(n) alignas(n)
 #define __shared__ static
 #define __constant__ static
