@@ -353,6 +353,23 @@ def config_c5(n_nodes=100_000, n_queues=64, n_new_jobs=400_000, seed=SEED) -> Ra
         queue_weight=_weights(n_queues), protected_fraction=0.5, name="C5")
 
 
+def unfeasible_runs_round(n_nodes: int) -> RawRound:
+    """Edge case: runs of jobs whose scheduling key is already known to be unfeasible
+    (queue_scheduler.go:339-349), shorter and longer than the iterator's 128-record fast-forward
+    step, ending in the middle of a step and at the end of a queue.  The oversized request (64 cpu)
+    fits no node and does not fit the packed key either."""
+    small, huge = rl(1, 4), rl(64, 4)
+    total = np.repeat(NODE_CPU32[:, None], n_nodes, axis=1)
+    runs = [(0, 3), (1, 700), (0, 5), (1, 130), (0, 2), (1, 127), (0, 1), (1, 129)]
+    cls = np.concatenate([np.full(n, c) for c, n in runs] + [np.zeros(40, np.int64)])
+    queue = np.concatenate([np.zeros(len(cls) - 40, np.int64), np.ones(40, np.int64)])  # + a queue of plain jobs
+    return RawRound(
+        node_total=total, node_allocatable=total.copy(), node_type=np.zeros(n_nodes), node_static_class=np.zeros(n_nodes),
+        class_request=np.stack([small, huge]), class_pc=np.zeros(2), class_static_row=np.zeros(2),
+        static_match=_bitmap([[0]], 1), type_match=_bitmap([[0]], 1),
+        job_class=cls, job_queue=queue, job_submit_time=np.arange(len(cls)), queue_weight=np.ones(2), name="unfeasible-runs")
+
+
 def scaled(name: str, scale: float) -> RawRound:
     """A geometrically similar, smaller instance of a named config (parity tests)."""
     f = {"C2": lambda: config_c2(max(8, int(10_000 * scale)), 16, max(64, int(100_000 * scale))),

@@ -112,3 +112,12 @@ def test_reference_queue_scheduler_tables(name):
         gt.run_queue_scheduler_case(QS[name], _emu_round_or_skip)
     except gt.UnsupportedCase as e:
         pytest.skip(f"outside device domain / not modelled: {e}")
+
+
+@pytest.mark.parametrize("n_nodes", [7, 401])
+def test_runs_of_known_unschedulable_jobs(n_nodes):
+    """synth.unfeasible_runs_round: skipped runs around the 128-record fast-forward step; the level
+    scan that proves the miss covers node counts that are not a multiple of its stride."""
+    r = synth.unfeasible_runs_round(n_nodes)
+    got, want = assert_parity(r.to_input(), r.name)
+    assert got.out.num_result_scheduled == want.out.num_result_scheduled == 11 + 40

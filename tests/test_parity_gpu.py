@@ -66,6 +66,13 @@ def test_scaled_configs(name, scale):
     assert got.out.num_result_scheduled == want.out.num_result_scheduled
 
 
+@pytest.mark.parametrize("n_nodes", [7, 401, 5000])
+def test_runs_of_known_unschedulable_jobs(n_nodes):
+    r = synth.unfeasible_runs_round(n_nodes)
+    got, want = assert_parity(r.to_input(), r.name)
+    assert got.out.num_result_scheduled == want.out.num_result_scheduled == 11 + 40
+
+
 def test_batch_mode_covers_the_plain_iterations_and_is_deterministic():
     """Most of a C3-shaped round runs in batch mode (ArmadaRoundStats.phase_cycles[4] = loop
     iterations executed there); repeating the round gives bit-identical results (no timing
