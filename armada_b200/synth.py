@@ -86,6 +86,7 @@ class RawRound:
     global_tokens: Optional[float] = None
     global_burst: int = 2**62
     global_inf: bool = True
+    indexed: Optional[Sequence[int]] = None             # indexed resources (default: all of them)
     name: str = ""
     _keep: list = field(default_factory=list)
 
@@ -103,8 +104,9 @@ class RawRound:
         inp = abi.RoundInput()
         inp.abi_version = abi.ABI_VERSION
         inp.num_resources = D
-        inp.num_indexed = len(INDEXED)
-        for i, (d, r) in enumerate(zip(INDEXED, RESOLUTION)):
+        indexed = list(self.indexed) if self.indexed is not None else INDEXED
+        inp.num_indexed = len(indexed)
+        for i, (d, r) in enumerate(zip(indexed, [RESOLUTION[INDEXED.index(d)] for d in indexed])):
             inp.indexed_resource[i] = d
             inp.indexed_resolution[i] = r
         inp.num_priorities = len(self.priorities)

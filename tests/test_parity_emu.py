@@ -121,3 +121,17 @@ def test_runs_of_known_unschedulable_jobs(n_nodes):
     r = synth.unfeasible_runs_round(n_nodes)
     got, want = assert_parity(r.to_input(), r.name)
     assert got.out.num_result_scheduled == want.out.num_result_scheduled == 11 + 40
+
+
+@pytest.mark.parametrize("seed,indexed", [(400, [synth.CPU, synth.MEM]), (401, [synth.CPU]), (402, [synth.MEM, synth.GPU]),
+                                          (403, [synth.CPU, synth.MEM])])
+def test_partly_indexed_resources(seed, indexed, lane_order):
+    """Not every resource is part of the best-fit key (nodedb indexedResources ⊂ resources): the
+    key no longer carries the whole row, so the SWAR shortcuts are off and the assignment table
+    keeps rows beside the keys (table_assign<false>, row-reading cursor refills)."""
+    batchy = seed != 403
+    r = synth.random_round(seed, n_nodes=120, n_queues=6, n_jobs=900, n_running=0 if batchy else 200, gangs=not batchy, priorities=not batchy)
+    r.indexed = indexed
+    got, _ = assert_parity(r.to_input(), f"{r.name} indexed={indexed}")
+    if batchy:
+        assert int(got.stats.phase_cycles[4]) > 0

@@ -73,6 +73,18 @@ def test_runs_of_known_unschedulable_jobs(n_nodes):
     assert got.out.num_result_scheduled == want.out.num_result_scheduled == 11 + 40
 
 
+@pytest.mark.parametrize("seed,indexed", [(400, [synth.CPU, synth.MEM]), (401, [synth.CPU]), (402, [synth.MEM, synth.GPU]),
+                                          (403, [synth.CPU, synth.MEM])])
+def test_partly_indexed_resources(seed, indexed):
+    """indexedResources ⊂ resources: no SWAR shortcuts, the assignment table keeps rows beside the keys."""
+    batchy = seed != 403
+    r = synth.random_round(seed, n_nodes=120, n_queues=6, n_jobs=900, n_running=0 if batchy else 200, gangs=not batchy, priorities=not batchy)
+    r.indexed = indexed
+    got, _ = assert_parity(r.to_input(), f"{r.name} indexed={indexed}")
+    if batchy:
+        assert int(got.stats.phase_cycles[4]) > 0
+
+
 def test_batch_mode_covers_the_plain_iterations_and_is_deterministic():
     """Most of a C3-shaped round runs in batch mode (ArmadaRoundStats.phase_cycles[4] = loop
     iterations executed there); repeating the round gives bit-identical results (no timing
