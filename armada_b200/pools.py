@@ -1,13 +1,21 @@
-"""Pools across ranks.
+"""One scheduling CYCLE = the pools of a cluster, one round each.
 
 The schedule phase of a round does not shard bit-exactly — one global cost heap orders every
-placement — but POOLS are independent units in the reference (`FairSchedulingAlgo.Schedule` walks
-them one after the other, scheduling_algo.go:129-160).  With one process per GPU, rank r schedules
-the pools `r, r + world, r + 2·world, …`; there is no data-path collective, only the per-pool
-results are gathered (`torch.distributed`, NCCL on the GPU box / gloo in the CPU tests)."""
+placement — but POOLS are independent units in the reference: `FairSchedulingAlgo.Schedule` walks
+them one after the other, each with its own NodeDb, queues and job set
+(scheduling/scheduling_algo.go:129-160).  With one process per GPU, rank r owns the pools
+`r, r + world, r + 2·world, …` of a FIXED cycle (strong scaling: the cycle does not grow with the
+number of GPUs), and the per-job claims of every pool are gathered on all ranks with one
+`all_gather` (NCCL over NVLink on the GPU box, gloo in the CPU tests) — what the leader needs to
+publish the cycle's result.
+
+Within a rank the pools of a cycle are software-pipelined over two device contexts: the host side
+of pool k+1 (validation, job-order ranking, staging, host→device copies) runs on a worker thread
+while pool k is scheduled on the device (`PoolCycle.schedule_cycle`)."""
 from __future__ import annotations
 
-from typing import Callable, List, Sequence
+import threading
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
@@ -19,20 +27,122 @@ def pools_of_rank(num_pools: int, rank: int, world: int) -> List[int]:
     return list(range(rank, num_pools, world))
 
 
+def summary_row(p: int, res) -> List[int]:
+    """[pool, scheduled, preempted, placements, checksum of the (job, node) claims]"""
+    state = np.asarray(res.job_state)
+    node = np.asarray(res.job_node).astype(np.int64)
+    sched = state == 1
+    return [p, int(res.out.num_result_scheduled), int(res.out.num_result_preempted), int(res.stats.placements),
+            int((np.nonzero(sched)[0].astype(np.int64) * 1000003 + node[sched]).sum() % (2**61 - 1))]
+
+
+def gather_claims(results: dict, num_pools: int, max_jobs: int, rank: int, world: int, dist=None) -> np.ndarray:
+    """Every rank ends up with claims[pool][job] = node the job was scheduled on this cycle
+    (0xFFFFFFFF = not scheduled): ONE all_gather of this rank's slab of per-pool claim rows.
+    `results` maps pool index -> RoundResult for the pools this rank owns."""
+    per_rank = (num_pools + world - 1) // world
+    slab = np.full((per_rank, max_jobs), 0xFFFFFFFF, dtype=np.uint32)
+    for i, p in enumerate(pools_of_rank(num_pools, rank, world)):
+        r = results[p]
+        node = np.asarray(r.job_node)
+        sched = np.asarray(r.job_state) == 1
+        row = np.where(sched, node, np.uint32(0xFFFFFFFF)).astype(np.uint32)
+        slab[i, : len(row)] = row
+    if dist is None or world == 1:
+        return slab[:num_pools]
+    import torch
+    t = torch.from_numpy(slab.view(np.int32))
+    nccl = dist.get_backend() == "nccl"
+    if nccl:
+        t = t.cuda(non_blocking=True)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t.contiguous())
+    out = torch.stack(parts).cpu().numpy().view(np.uint32)  # [world][per_rank][max_jobs]
+    claims = np.empty((num_pools, max_jobs), np.uint32)
+    for p in range(num_pools):
+        claims[p] = out[p % world, p // world]
+    return claims
+
+
+class PoolCycle:
+    """The pools this rank owns, scheduled through `make_round()` device contexts (DeviceRound)."""
+
+    def __init__(self, pool_inputs: Sequence, rank: int, world: int, make_round: Callable):
+        self.inputs = pool_inputs
+        self.rank, self.world = rank, world
+        self.mine = pools_of_rank(len(pool_inputs), rank, world)
+        self.make_round = make_round
+        self._resident: Optional[list] = None
+        self._pipe: Optional[list] = None
+
+    # ---- inputs resident on the device: one context per owned pool ---------------------------------
+    def upload_resident(self) -> None:
+        if self._resident is None:
+            self._resident = [self.make_round() for _ in self.mine]
+        for dev, p in zip(self._resident, self.mine):
+            dev.upload(self.inputs[p])
+
+    def run_resident(self) -> list:
+        """One cycle with resident inputs; returns the per-pool device statistics."""
+        return [dev.run() for dev in self._resident]
+
+    def download_resident(self, i: int, res=None):
+        return self._resident[i].download(res)
+
+    # ---- host buffers in, host buffers out: two contexts, upload of pool k+1 under the run of pool k
+    def schedule_cycle(self, results: Optional[dict] = None) -> dict:
+        from .model import RoundResult
+        if self._pipe is None:
+            self._pipe = [self.make_round(), self.make_round()]
+        out = {} if results is None else results
+        if not self.mine:
+            return out
+        err: List[BaseException] = []
+
+        def up(slot: int, p: int):
+            try:
+                self._pipe[slot].upload(self.inputs[p])
+            except BaseException as e:  # surfaced on the main thread
+                err.append(e)
+
+        up(0, self.mine[0])
+        for k, p in enumerate(self.mine):
+            if err:
+                raise err[0]
+            nxt = None
+            if k + 1 < len(self.mine):
+                nxt = threading.Thread(target=up, args=((k + 1) & 1, self.mine[k + 1]))
+                nxt.start()
+            dev = self._pipe[k & 1]
+            res = out.get(p)
+            if res is None:
+                res = RoundResult(self.inputs[p])
+            res.stats = dev.run()
+            dev.download(res)
+            out[p] = res
+            if nxt is not None:
+                nxt.join()
+        if err:
+            raise err[0]
+        return out
+
+    def close(self):
+        for d in (self._resident or []) + (self._pipe or []):
+            d.close()
+        self._resident = self._pipe = None
+
+
 def schedule_pools(pool_inputs: Sequence, rank: int, world: int, schedule: Callable, dist=None):
     """Schedule this rank's pools with `schedule(input) -> RoundResult` and return, on every rank,
-    one summary row per pool: [pool, scheduled, preempted, placements, checksum of (job, node)].
-
-    `dist` is `torch.distributed` (already initialised) or None for a single process."""
+    (summary rows [pool, scheduled, preempted, placements, checksum], claims[pool][job])."""
     mine = pools_of_rank(len(pool_inputs), rank, world)
     rows = np.zeros((len(pool_inputs), 5), dtype=np.int64)
+    results = {}
     for p in mine:
-        res = schedule(pool_inputs[p])
-        state = np.asarray(res.job_state)
-        node = np.asarray(res.job_node).astype(np.int64)
-        sched = state == 1
-        rows[p] = [p, int(res.out.num_result_scheduled), int(res.out.num_result_preempted), int(res.stats.placements),
-                   int((np.nonzero(sched)[0].astype(np.int64) * 1000003 + node[sched]).sum() % (2**61 - 1))]
+        results[p] = schedule(pool_inputs[p])
+        rows[p] = summary_row(p, results[p])
+    max_jobs = max(int(i.num_jobs) for i in pool_inputs)
+    claims = gather_claims(results, len(pool_inputs), max_jobs, rank, world, dist)
     if dist is not None and world > 1:
         import torch
         t = torch.from_numpy(rows)
@@ -40,4 +150,4 @@ def schedule_pools(pool_inputs: Sequence, rank: int, world: int, schedule: Calla
             t = t.cuda()
         dist.all_reduce(t)  # every pool is written by exactly one rank, the others contribute zeros
         rows = t.cpu().numpy()
-    return rows
+    return rows, claims

@@ -249,14 +249,20 @@ typedef struct {
                                     0 queue arg-min, 1 gang bookkeeping+constraints, 2 node
                                     selection, 3 node row update, 4 (see batch_cycles),
                                     5 result algebra, 6 iterator advance, 7 cost update       */
-  uint64_t batch_cycles[8];      /* device only: batch mode (many loop iterations at once): SM
-                                    cycles in 0 item build, 1 horizon, 2 merge ranks, 3 node
-                                    assignment, 4 commit, 5 re-peek; 6 = number of batches,
-                                    7 unused.  phase_cycles[4] = iterations run in batch mode */
-  uint64_t batch_debug[8];       /* device only: spare debug counters */
+  uint64_t batch_cycles[8];      /* device only: batch mode (many loop iterations at once), SM cycles of
+                                    the index warps in 0 item build, 1 horizon, 2 merge ranks, 3 waiting
+                                    for the assignment loop, 4 apply + commit, 5 control; 6 = number of
+                                    batches, 7 pipeline epilogue.  phase_cycles[4] = iterations run in
+                                    batch mode */
+  uint64_t batch_debug[8];       /* device only: 0 assignment loop busy cycles, 1 assignment loop cycles
+                                    waiting for records, 2 pipeline runs, 3 batches cut short, 4.. spare */
 } ArmadaRoundStats;
 
 /* ---- product entry points (libarmada_b200.so) ------------------------------------- */
+/* Thread safety: one ArmadaRound handle is used by one thread at a time.  Different handles may be
+ * used from different threads concurrently, also on the same device: their armada_round_run calls
+ * are serialised inside the library (per device), uploads/downloads overlap with a running round
+ * of another handle (armada_b200/pools.py pipelines the pools of a cycle this way). */
 typedef struct ArmadaRound ArmadaRound;
 
 /* Bind to CUDA device `device` and allocate the per-round context. */

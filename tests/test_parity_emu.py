@@ -135,3 +135,29 @@ def test_partly_indexed_resources(seed, indexed, lane_order):
     got, _ = assert_parity(r.to_input(), f"{r.name} indexed={indexed}")
     if batchy:
         assert int(got.stats.phase_cycles[4]) > 0
+
+
+@pytest.mark.parametrize("wq,seed", [(8, 500), (8, 501), (16, 502), (8, 503)])
+def test_long_batch_pipelines(wq, seed, lane_order):
+    """Small batches (ARMADA_BT_WQ test knob: items per queue per batch) make one pipeline run span
+    many batches: batch k+1 is produced from the speculative queue state while batch k is assigned,
+    jobs that find no node cut a batch short (the batch built behind it is dropped), runs of
+    known-unschedulable jobs sit between committed items."""
+    os.environ["ARMADA_BT_WQ"] = str(wq)
+    try:
+        dev = emu_lib.emu_round()
+        if seed == 503:
+            r = synth.unfeasible_runs_round(7)
+        else:
+            r = synth.random_round(seed, n_nodes=24 + 10 * (seed % 3), n_queues=5 + seed % 4, n_jobs=1400, n_running=0, gangs=seed == 502,
+                                   priorities=False, round_limit=seed == 501)
+        inp = r.to_input()
+        want = oracle_lib.round_schedule(inp)
+        got = dev.schedule(inp)
+        bad = got.diff(want)
+        assert not bad, f"{r.name}: emulated kernel != oracle:\n  " + "\n  ".join(bad)
+        if seed != 503:
+            assert int(got.stats.batch_cycles[6]) >= {500: 8, 501: 2, 502: 3}[seed], "expected several batches per pipeline run"
+        dev.close()
+    finally:
+        os.environ.pop("ARMADA_BT_WQ", None)

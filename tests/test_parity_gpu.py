@@ -154,6 +154,24 @@ def test_unsupported_domain_fails_loudly():
     assert ei.value.status == abi.E_UNSUPPORTED
 
 
+@pytest.mark.parametrize("name", ["C2", "C3", "C4"])
+def test_full_size_parity(name):
+    """The BASELINE.json configurations at their stated size, bit-exact on every output array
+    against the oracle (C3 is the benchmarked configuration; the oracle needs 1–3 s for it)."""
+    r = {"C2": synth.config_c2, "C3": synth.config_c3, "C4": synth.config_c4}[name]()
+    got, want = assert_parity(r.to_input(), f"{name} full size")
+    assert got.out.num_result_scheduled == want.out.num_result_scheduled > 0
+
+
+def test_c5_largest_oracle_scale_parity():
+    """C5 (90 % utilisation, eviction round): the reference's fair-preemption walk is quadratic in
+    the number of evicted jobs, so the oracle is run at the largest scale it finishes within about
+    a minute (10k nodes); the full-size round is covered by bench.py's extra workloads."""
+    r = synth.scaled("C5", 0.1)
+    got, want = assert_parity(r.to_input(), "C5@0.1")
+    assert got.out.num_result_preempted == want.out.num_result_preempted
+
+
 def test_full_size_properties():
     """BASELINE-size C3 through size-independent properties: no oversubscription, every scheduled
     job fits its node, conservation of resources, idempotence of a second run."""
