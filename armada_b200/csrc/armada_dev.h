@@ -39,6 +39,7 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int32_t key_width[ARMADA_MAX_RESOURCES];  // per indexed resource i: field width in bits
   unsigned long long key_guard;             // one always-zero bit above every field (0 = no guard bits)
   int32_t swar_ok;                          // guard bits present and every resource is indexed
+  int32_t k32_ok;                           // … and the resource fields without guard bits fit 26 bits (32-bit compare keys)
   int32_t priorities[ARMADA_MAX_PRIORITIES];
   ArmadaPriorityClass pcs[ARMADA_MAX_PRIORITY_CLASSES];
   int64_t total_resources[ARMADA_MAX_RESOURCES];

@@ -137,8 +137,18 @@ def test_partly_indexed_resources(seed, indexed, lane_order):
         assert int(got.stats.phase_cycles[4]) > 0
 
 
+@pytest.fixture(params=["k32", "k64"])
+def compare_key(request):
+    """The assignment loop compares 32-bit compact keys when the resource fields fit 26 bits
+    (ARMADA_NO_K32 forces the general 64-bit form)."""
+    if request.param == "k64":
+        os.environ["ARMADA_NO_K32"] = "1"
+    yield request.param
+    os.environ.pop("ARMADA_NO_K32", None)
+
+
 @pytest.mark.parametrize("wq,seed", [(8, 500), (8, 501), (16, 502), (8, 503)])
-def test_long_batch_pipelines(wq, seed, lane_order):
+def test_long_batch_pipelines(wq, seed, lane_order, compare_key):
     """Small batches (ARMADA_BT_WQ test knob: items per queue per batch) make one pipeline run span
     many batches: batch k+1 is produced from the speculative queue state while batch k is assigned,
     jobs that find no node cut a batch short (the batch built behind it is dropped), runs of

@@ -32,4 +32,5 @@ with DeviceRound(0) as dev:
                           "batched": int(best.phase_cycles[4]), "batches": int(best.batch_cycles[6]),
                           "placements_per_s": round(best.placements / (best.device_ms / 1e3)),
                           "batch_cycles_per_iter": [round(int(best.batch_cycles[i]) / it, 1) for i in range(6)],
+                          "chain_busy_wait_per_iter": [round(int(best.batch_debug[i]) / it, 1) for i in range(2)], "runs_cut": [int(best.batch_debug[2]), int(best.batch_debug[3])],
                           "fair_scans": int(best.fair_preemption_scans), "ev1": int(best.evicted_pass1), "ev2": int(best.evicted_pass2)}), flush=True)
