@@ -39,6 +39,7 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int32_t key_width[ARMADA_MAX_RESOURCES];  // per indexed resource i: field width in bits
   unsigned long long key_guard;             // one always-zero bit above every field (0 = no guard bits)
   int32_t swar_ok;                          // guard bits present and every resource is indexed
+  int32_t park_mates;                       // measurement knob (ARMADA_PARK_MATES): see Batch::produce
   int32_t k32_ok;                           // … and the resource fields without guard bits fit 26 bits (32-bit compare keys)
   int32_t priorities[ARMADA_MAX_PRIORITIES];
   ArmadaPriorityClass pcs[ARMADA_MAX_PRIORITY_CLASSES];
@@ -142,7 +143,8 @@ struct DevPtrs {
   uint32_t* bt_pos;                // stream position of the item
   uint32_t* bt_rank;               // merged position
   uint2* bt_seq;                   // merged sequence: {job, class}
-  uint32_t* bt_node;               // node of every placement of the batch, in merged order
+  uint32_t* bt_node;               // (unused)
+  int64_t* bt_asum;                // [2][Q][MAX_RESOURCES] requests of every queue's items below the horizon, per batch buffer
   uint32_t* undo_log;              // [5 * J] txn undo records
   // fair preemption scratch
   int64_t* fp_avail;               // [D][N]

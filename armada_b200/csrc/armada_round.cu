@@ -40,6 +40,7 @@ static __device__ __forceinline__ void armada_emu_yield() {}
 #include <mutex>
 #include <chrono>
 #include <thread>
+#include <type_traits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>

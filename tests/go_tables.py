@@ -32,6 +32,13 @@ class Rl(dict):
     """A quantity map (resource name → quantity string/number)."""
 
 
+class _Fresh:
+    """An identifier whose value is rebuilt on every use (config objects are mutated by With…Config)."""
+
+    def __init__(self, make):
+        self.make = make
+
+
 class Env:
     """Evaluation environment: Go identifier / function name → Python value."""
 
@@ -55,6 +62,9 @@ class Env:
             "v1.NodeSelectorOpIn": "In",
             "armadaconfiguration.GangIdAnnotation": "armadaproject.io/gangId",
             "armadaconfiguration.GangCardinalityAnnotation": "armadaproject.io/gangCardinality",
+            # queue_scheduler_test.go:33-34 (a local of the test function): the reference's DEFAULT
+            # ordering (config.yaml:85 enablePreferLargeJobOrdering: false); a fresh copy per use
+            "schedulingConfigWithPreferLargeJobDisabled": _Fresh(lambda: fx.test_scheduling_config(enable_prefer_large_job_ordering=False)),
         }
         self.calls: Dict[str, Callable] = {
             "testfixtures.IntRange": lambda a, b: list(range(a, b + 1)),
@@ -186,7 +196,8 @@ class Env:
             raise UnsupportedCase(n["unsupported"])
         if "id" in n:
             if n["id"] in self.ids:
-                return self.ids[n["id"]]
+                v = self.ids[n["id"]]
+                return v.make() if isinstance(v, _Fresh) else v
             raise UnsupportedCase(f"identifier {n['id']}")
         if "neg" in n:
             return -self.ev(n["neg"])

@@ -33,4 +33,6 @@ with DeviceRound(0) as dev:
                           "placements_per_s": round(best.placements / (best.device_ms / 1e3)),
                           "batch_cycles_per_iter": [round(int(best.batch_cycles[i]) / it, 1) for i in range(6)],
                           "chain_busy_wait_per_iter": [round(int(best.batch_debug[i]) / it, 1) for i in range(2)], "runs_cut": [int(best.batch_debug[2]), int(best.batch_debug[3])],
+                          "slow_steps": int(best.batch_debug[4]), "cycles_per_slow_step": round(int(best.batch_debug[5]) / max(1, int(best.batch_debug[4]))),
+                          "refills": int(best.batch_debug[6]), "cycles_per_refill": round(int(best.batch_debug[7]) / max(1, int(best.batch_debug[6]))),
                           "fair_scans": int(best.fair_preemption_scans), "ev1": int(best.evicted_pass1), "ev2": int(best.evicted_pass2)}), flush=True)
