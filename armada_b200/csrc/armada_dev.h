@@ -39,6 +39,9 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int32_t key_width[ARMADA_MAX_RESOURCES];  // per indexed resource i: field width in bits
   unsigned long long key_guard;             // one always-zero bit above every field (0 = no guard bits)
   int32_t swar_ok;                          // guard bits present and every resource is indexed
+  int32_t exact;                            // exact mode (see armada_host.inc "domain"): raw units everywhere, probes are literal
+                                            // ordered walks over per-level rounded keys (Ctl::scan_probe_exact), no sorted index / batches
+  int64_t index_res[ARMADA_MAX_RESOURCES];  // exact mode: index resolution of the i-th indexed resource (raw units)
   int32_t park_mates;                       // measurement knob (ARMADA_PARK_MATES): see Batch::produce
   int32_t k32_ok;                           // … and the resource fields without guard bits fit 26 bits (32-bit compare keys)
   int32_t priorities[ARMADA_MAX_PRIORITIES];
@@ -76,6 +79,11 @@ struct DevPtrs {
   const uint4* q_rec;              // [#queued] stream records aligned with queued_order
   uint4* ev_rec;                   // [J] stream records aligned with evq_jobs (per pass)
   const uint32_t* static_match;    // [rows][sw]
+  const uint32_t* type_match;      // exact mode: [rows][tw] NodeTypeJobRequirementsMet
+  const uint32_t* node_type;       // exact mode: [N] dense node type
+  const uint32_t* node_xrank;      // exact mode: [N] rank of the node in (node type, NodeFactory index) order
+  const uint32_t* node_of_xrank;   // exact mode: [N] inverse of node_xrank
+  unsigned long long* xkey;        // exact mode: [PL][N] rounded best-fit key of every node at every level
   const uint32_t* job_class;       // [J]
   const uint32_t* job_queue;       // [J]
   const uint32_t* job_gang;        // [J]

@@ -457,6 +457,28 @@ __global__ void k_g0_keys(DevCfg c, DevPtrs P) {
   P.g0[n] = neg ? (marker | n) : key;
 }
 
+// Exact mode: the rounded best-fit key of one node at one level (nodedb/encoding.go:37-58):
+// field i = floor(allocatable_i / resolution_i) + 1, 0 for a negative row (every negative value sorts
+// before every non-negative one and is below every request), low bits = the node's rank in
+// (node type, NodeFactory index) order.  Go's roundQuantityToResolution truncates, which for the
+// non-negative values that matter is the floor.
+__device__ __forceinline__ unsigned long long xfield_of(int64_t v, int64_t res) {
+  if (v < 0) return 0ull;
+  long long q = (long long)((double)v / (double)res);  // estimate, corrected below
+  while (q * res > v) --q;
+  while ((q + 1) * res <= v) ++q;
+  return (unsigned long long)q + 1ull;
+}
+__global__ void k_xkeys(DevCfg c, DevPtrs P) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)c.PL * c.N) return;
+  const size_t p = i / c.N, n = i - p * c.N;
+  unsigned long long key = P.node_xrank[n];
+  for (int k = 0; k < c.R; ++k)
+    key |= xfield_of(P.alloc[(p * c.D + c.indexed_resource[k]) * c.N + n], c.index_res[k]) << c.key_shift[k];
+  P.xkey[i] = key;
+}
+
 // static class of the node at every G0 position
 __global__ void k_g0_sc(DevCfg c, DevPtrs P) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

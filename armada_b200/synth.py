@@ -87,6 +87,7 @@ class RawRound:
     global_burst: int = 2**62
     global_inf: bool = True
     indexed: Optional[Sequence[int]] = None             # indexed resources (default: all of them)
+    resolution: Optional[Sequence[int]] = None          # index resolution per entry of `indexed` (default: TestResources)
     name: str = ""
     _keep: list = field(default_factory=list)
 
@@ -106,7 +107,8 @@ class RawRound:
         inp.num_resources = D
         indexed = list(self.indexed) if self.indexed is not None else INDEXED
         inp.num_indexed = len(indexed)
-        for i, (d, r) in enumerate(zip(indexed, [RESOLUTION[INDEXED.index(d)] for d in indexed])):
+        res = list(self.resolution) if self.resolution is not None else [RESOLUTION[INDEXED.index(d)] for d in indexed]
+        for i, (d, r) in enumerate(zip(indexed, res)):
             inp.indexed_resource[i] = d
             inp.indexed_resolution[i] = r
         inp.num_priorities = len(self.priorities)
@@ -382,7 +384,8 @@ def scaled(name: str, scale: float) -> RawRound:
 
 
 def random_round(seed: int, n_nodes=60, n_queues=5, n_jobs=400, n_running=120, gangs=True, priorities=True,
-                 protected_fraction=0.0, lookback=0, round_limit=False, queue_limits=False, away=False) -> RawRound:
+                 protected_fraction=0.0, lookback=0, round_limit=False, queue_limits=False, away=False,
+                 unaligned=False) -> RawRound:
     """Small random round inside the device fast-path domain exercising every mechanism:
     several node kinds, priority classes 0–3 (incl. non-preemptible), running jobs at various
     priorities (⇒ eviction, fair-share and urgency preemption), gangs, limits, lookback."""
@@ -396,7 +399,17 @@ def random_round(seed: int, n_nodes=60, n_queues=5, n_jobs=400, n_running=120, g
     total[MEM, small & (kind == 0)] = 128 * GI
     npc = len(PCS) if priorities else 1
     shapes = [rl(1, 4), rl(1, 16), rl(2, 8), rl(4, 16), rl(8, 64), rl(16, 128), rl(8, 128, 1), rl(32, 256), rl(1, 1, 1)]
-    rows = [0, 0, 0, 0, 0, 0, 1, 0, 1]
+    resolution = None
+    if unaligned:
+        # the reference's default index resolutions (config/scheduler/config.yaml:116-124: cpu 100m, memory
+        # 100Mi, gpu 1) with requests and node sizes that are NOT multiples of them (250m, 4Gi, 256Gi …),
+        # node sizes that differ by less than one resolution step, allocatable below total
+        resolution = [100, 100 * MI, 1000]
+        shapes = [rl(0.25, 4), rl(1, 4), rl(1.5, 16), rl(2, 8.5), rl(3.75, 16), rl(8, 64), rl(16, 128), rl(8, 128, 1), rl(30.25, 250), rl(1, 1, 1)]
+        jitter = rng.integers(0, 4, n_nodes)
+        total[CPU] -= jitter * 30           # 30m steps: several nodes per rounded cpu bucket
+        total[MEM] -= rng.integers(0, 5, n_nodes) * 37 * MI
+    rows = [0, 0, 0, 0, 0, 0, 1, 0, 1] if not unaligned else [0, 0, 1, 0, 0, 0, 0, 1, 0, 1]
     cls_req, cls_pc, cls_row = [], [], []
     pc_away = None
     away_rows = []
@@ -481,9 +494,15 @@ def random_round(seed: int, n_nodes=60, n_queues=5, n_jobs=400, n_running=120, g
     if queue_limits:
         qlimit = np.full((n_queues, len(pcs), D), I64_MAX, np.int64)
         qlimit[:, :, CPU] = int(total[CPU].sum() * 0.2)
+    allocatable = total.copy()
+    node_index = None
+    if unaligned:
+        allocatable[MEM] -= rng.integers(0, 3, n_nodes) * 512 * MI   # kubelet reservations: allocatable < total
+        allocatable = np.maximum(allocatable, free * 0 + (total - free))  # never below what already runs
+        node_index = rng.permutation(n_nodes)                         # NodeFactory index order != node id order
     return RawRound(
-        node_total=total, node_allocatable=total.copy(), node_type=kind, node_static_class=kind,
-        num_node_types=2, num_static_classes=2,
+        node_total=total, node_allocatable=allocatable, node_type=kind, node_static_class=kind,
+        num_node_types=2, num_static_classes=2, node_index=node_index, resolution=resolution,
         class_request=np.stack(cls_req), class_pc=np.array(cls_pc), class_static_row=np.array(cls_row),
         class_away_row=np.array(away_rows, np.uint32), static_match=static_match, type_match=static_match.copy(),
         job_class=job_class, job_queue=job_queue, job_submit_time=rng.permutation(J), job_node=job_node,
@@ -493,3 +512,18 @@ def random_round(seed: int, n_nodes=60, n_queues=5, n_jobs=400, n_running=120, g
         queue_weight=np.array([1.0, 0.5, 0.25, 2.0])[np.arange(n_queues) % 4], pcs=tuple(pcs), pc_away=pc_away,
         priorities=tuple(prios), protected_fraction=protected_fraction, max_queue_lookback=lookback,
         round_limit=limit, queue_limit=qlimit, name=f"random-{seed}")
+
+
+def rounding_round() -> RawRound:
+    """gang_scheduler_test.go:244-262 ("jobs of size not a multiple of the resolution blocks scheduling
+    new jobs"): 3 × Test32CpuNode, index resolutions cpu 17 / memory 128Mi, four 16-cpu / 128Gi jobs.
+    A node with 16 cpu left has a ROUNDED quantity of 0 and the iterator's lower bound (16) skips it,
+    so only three jobs are placed although the fourth would fit."""
+    N, J = 3, 4
+    total = np.repeat(NODE_CPU32[:, None], N, axis=1)
+    return RawRound(
+        node_total=total, node_allocatable=total.copy(), node_type=np.zeros(N), node_static_class=np.zeros(N),
+        class_request=rl(16, 128)[None, :], class_pc=np.zeros(1), class_static_row=np.zeros(1),
+        static_match=_bitmap([[0]], 1), type_match=_bitmap([[0]], 1),
+        job_class=np.zeros(J), job_queue=np.zeros(J), job_submit_time=np.arange(J), queue_weight=np.ones(1),
+        indexed=[CPU, MEM], resolution=[17000, 128 * MI], name="rounding")

@@ -171,3 +171,37 @@ def test_long_batch_pipelines(wq, seed, lane_order, compare_key):
         dev.close()
     finally:
         os.environ.pop("ARMADA_BT_WQ", None)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_exact_mode_unaligned_rounds(seed, lane_order):
+    """Inputs outside the fast domain run in exact mode: the reference's default index resolutions
+    (cpu 100m, memory 100Mi) with 250m / 4Gi-style requests, node sizes that are not multiples of
+    them, allocatable < total, a NodeFactory index order that differs from the node-id order, classes
+    that match several node types.  Every probe is the literal ordered walk of nodeiteration.go."""
+    r = synth.random_round(seed, away=(seed % 4 == 1), n_nodes=40 + 13 * (seed % 7), n_jobs=300 + 50 * (seed % 5),
+                           n_running=80 + 20 * (seed % 4), protected_fraction=0.5 if seed % 3 == 2 else 0.0,
+                           round_limit=(seed % 6 == 3), queue_limits=(seed % 6 == 4), lookback=40 if seed % 5 == 1 else 0, unaligned=True)
+    assert_parity(r.to_input(), r.name)
+
+
+def test_exact_mode_resolution_rounding_blocks_a_feasible_node():
+    """gang_scheduler_test.go:244-262 on the device path: the fourth job fits a node but the rounded
+    index key hides that node from the iterator."""
+    got, want = assert_parity(synth.rounding_round().to_input(), "rounding")
+    assert got.out.num_result_scheduled == want.out.num_result_scheduled == 3
+    assert int((got.job_state == abi.JOB_FAILED).sum()) == 1
+
+
+@pytest.mark.parametrize("seed", [0, 5])
+def test_exact_mode_forced_on_aligned_rounds(seed):
+    """ARMADA_FORCE_EXACT: the literal walk on inputs the fast path also accepts gives the same round."""
+    os.environ["ARMADA_FORCE_EXACT"] = "1"
+    try:
+        dev = emu_lib.emu_round()
+        r = synth.random_round(seed, away=(seed % 4 == 1), n_nodes=60, n_jobs=350, n_running=90, protected_fraction=0.5 if seed else 0.0)
+        inp = r.to_input()
+        assert not dev.schedule(inp).diff(oracle_lib.round_schedule(inp))
+        dev.close()
+    finally:
+        os.environ.pop("ARMADA_FORCE_EXACT", None)

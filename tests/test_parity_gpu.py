@@ -145,13 +145,36 @@ def test_reference_queue_scheduler_tables_on_device(name):
         pytest.skip(f"outside device domain / not modelled: {e}")
 
 
-def test_unsupported_domain_fails_loudly():
-    r = synth.random_round(1)
-    r.class_request = r.class_request.copy()
-    r.class_request[0, synth.CPU] = 1500  # not a multiple of the 1-cpu index resolution
+def test_unsupported_input_fails_loudly():
+    """What the device cannot hold is refused with a status code, never computed wrongly: more queues
+    than the shared-memory queue table has rows."""
+    r = synth.random_round(1, n_queues=129)
     with pytest.raises(abi.ArmadaError) as ei:
         cuda_round(r.to_input())
     assert ei.value.status == abi.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_exact_mode_unaligned_rounds(seed):
+    """The reference's default index resolutions (config/scheduler/config.yaml:116-124: cpu 100m, memory
+    100Mi) with 250m / 4Gi-style requests, node sizes that are not multiples of them, allocatable <
+    total, NodeFactory index order != node-id order, classes matching several node types: exact mode
+    (literal ordered walks, nodeiteration.go:318-382) — no E_UNSUPPORTED, bit-exact."""
+    r = synth.random_round(seed, away=(seed % 4 == 1), n_nodes=40 + 13 * (seed % 7), n_jobs=300 + 50 * (seed % 5),
+                           n_running=80 + 20 * (seed % 4), protected_fraction=0.5 if seed % 3 == 2 else 0.0,
+                           round_limit=(seed % 6 == 3), queue_limits=(seed % 6 == 4), lookback=40 if seed % 5 == 1 else 0, unaligned=True)
+    assert_parity(r.to_input(), r.name)
+
+
+def test_exact_mode_many_nodes():
+    r = synth.random_round(77, n_nodes=3000, n_queues=7, n_jobs=2500, n_running=1500, protected_fraction=0.5, unaligned=True)
+    assert_parity(r.to_input(), r.name)
+
+
+def test_exact_mode_resolution_rounding_blocks_a_feasible_node():
+    """gang_scheduler_test.go:244-262: the rounded index key hides a node that would fit."""
+    got, want = assert_parity(synth.rounding_round().to_input(), "rounding")
+    assert got.out.num_result_scheduled == want.out.num_result_scheduled == 3
 
 
 @pytest.mark.parametrize("name", ["C2", "C3", "C4"])
