@@ -16,7 +16,7 @@ NONE = 0xFFFFFFFF
 NO_PRIORITY = -(2**31)
 
 # status codes
-OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NO_DEVICE, E_INTERNAL, E_STATE = range(7)
+OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NO_DEVICE, E_INTERNAL, E_STATE, E_DEADLINE = range(8)
 # job states
 JOB_NONE, JOB_SCHEDULED, JOB_PREEMPTED, JOB_RESCHEDULED, JOB_FAILED, JOB_SCHEDULED_AND_EVICTED = range(6)
 # scheduling methods
@@ -187,6 +187,8 @@ def declare_prototypes(lib: C.CDLL) -> None:
     lib.armada_round_upload.restype = C.c_int32
     lib.armada_round_run.argtypes = [vp, C.POINTER(RoundStats)]
     lib.armada_round_run.restype = C.c_int32
+    lib.armada_round_run_deadline.argtypes = [vp, C.POINTER(RoundStats), C.c_uint64]
+    lib.armada_round_run_deadline.restype = C.c_int32
     lib.armada_round_download.argtypes = [vp, C.POINTER(RoundOutput)]
     lib.armada_round_download.restype = C.c_int32
     lib.armada_round_destroy.argtypes = [vp]
@@ -220,6 +222,7 @@ PRODUCT_SYMBOLS = [
     "armada_round_create",
     "armada_round_upload",
     "armada_round_run",
+    "armada_round_run_deadline",
     "armada_round_download",
     "armada_round_destroy",
     "armada_round_schedule",

@@ -39,6 +39,7 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
   int32_t key_width[ARMADA_MAX_RESOURCES];  // per indexed resource i: field width in bits
   unsigned long long key_guard;             // one always-zero bit above every field (0 = no guard bits)
   int32_t swar_ok;                          // guard bits present and every resource is indexed
+  int32_t cls_global;                       // the job-class table is in global memory (more than 256 classes)
   int32_t exact;                            // exact mode (see armada_host.inc "domain"): raw units everywhere, probes are literal
                                             // ordered walks over per-level rounded keys (Ctl::scan_probe_exact), no sorted index / batches
   int64_t index_res[ARMADA_MAX_RESOURCES];  // exact mode: index resolution of the i-th indexed resource (raw units)
@@ -79,6 +80,7 @@ struct DevPtrs {
   const uint4* q_rec;              // [#queued] stream records aligned with queued_order
   uint4* ev_rec;                   // [J] stream records aligned with evq_jobs (per pass)
   const uint32_t* static_match;    // [rows][sw]
+  unsigned char* cls_glob;         // [C] ClassRec table when it does not fit shared memory (DevCfg.cls_global)
   const uint32_t* type_match;      // exact mode: [rows][tw] NodeTypeJobRequirementsMet
   const uint32_t* node_type;       // exact mode: [N] dense node type
   const uint32_t* node_xrank;      // exact mode: [N] rank of the node in (node type, NodeFactory index) order

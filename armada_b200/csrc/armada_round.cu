@@ -37,6 +37,7 @@ static __device__ __forceinline__ void armada_emu_yield() {}
 #include <algorithm>
 #include <atomic>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
 #include <chrono>
 #include <thread>

@@ -9,9 +9,10 @@ number of GPUs), and the per-job claims of every pool are gathered on all ranks 
 `all_gather` (NCCL over NVLink on the GPU box, gloo in the CPU tests) — what the leader needs to
 publish the cycle's result.
 
-Within a rank the pools of a cycle are software-pipelined over two device contexts: the host side
-of pool k+1 (validation, job-order ranking, staging, host→device copies) runs on a worker thread
-while pool k is scheduled on the device (`PoolCycle.schedule_cycle`)."""
+Within a rank the pools of a cycle run CONCURRENTLY: a round is one persistent CTA on one SM, the
+library keeps up to 8 rounds of different device contexts in flight per GPU (include/armada_b200.h,
+"thread safety"), so every owned pool gets its own context and its own host thread (upload → run →
+download); the host side of one pool overlaps with the device rounds of the others."""
 from __future__ import annotations
 
 import threading
@@ -83,45 +84,59 @@ class PoolCycle:
             dev.upload(self.inputs[p])
 
     def run_resident(self) -> list:
-        """One cycle with resident inputs; returns the per-pool device statistics."""
-        return [dev.run() for dev in self._resident]
+        """One cycle with resident inputs, the owned pools concurrently; returns the per-pool device
+        statistics (every round is timed on its own stream)."""
+        out: list = [None] * len(self._resident)
+        err: List[BaseException] = []
+
+        def go(i):
+            try:
+                out[i] = self._resident[i].run()
+            except BaseException as e:
+                err.append(e)
+
+        ts = [threading.Thread(target=go, args=(i,)) for i in range(1, len(self._resident))]
+        for t in ts:
+            t.start()
+        if self._resident:
+            go(0)
+        for t in ts:
+            t.join()
+        if err:
+            raise err[0]
+        return out
 
     def download_resident(self, i: int, res=None):
         return self._resident[i].download(res)
 
-    # ---- host buffers in, host buffers out: two contexts, upload of pool k+1 under the run of pool k
+    # ---- host buffers in, host buffers out: one context and one host thread per owned pool ------------
     def schedule_cycle(self, results: Optional[dict] = None) -> dict:
         from .model import RoundResult
         if self._pipe is None:
-            self._pipe = [self.make_round(), self.make_round()]
+            self._pipe = [self.make_round() for _ in self.mine]
         out = {} if results is None else results
-        if not self.mine:
-            return out
         err: List[BaseException] = []
 
-        def up(slot: int, p: int):
+        def go(i: int, p: int):
             try:
-                self._pipe[slot].upload(self.inputs[p])
-            except BaseException as e:  # surfaced on the main thread
+                dev = self._pipe[i]
+                res = out.get(p)
+                if res is None:
+                    res = RoundResult(self.inputs[p])
+                dev.upload(self.inputs[p])
+                res.stats = dev.run()
+                dev.download(res)
+                out[p] = res
+            except BaseException as e:  # surfaced on the calling thread
                 err.append(e)
 
-        up(0, self.mine[0])
-        for k, p in enumerate(self.mine):
-            if err:
-                raise err[0]
-            nxt = None
-            if k + 1 < len(self.mine):
-                nxt = threading.Thread(target=up, args=((k + 1) & 1, self.mine[k + 1]))
-                nxt.start()
-            dev = self._pipe[k & 1]
-            res = out.get(p)
-            if res is None:
-                res = RoundResult(self.inputs[p])
-            res.stats = dev.run()
-            dev.download(res)
-            out[p] = res
-            if nxt is not None:
-                nxt.join()
+        ts = [threading.Thread(target=go, args=(i, p)) for i, p in list(enumerate(self.mine))[1:]]
+        for t in ts:
+            t.start()
+        if self.mine:
+            go(0, self.mine[0])
+        for t in ts:
+            t.join()
         if err:
             raise err[0]
         return out

@@ -35,9 +35,14 @@ class DeviceRound:
         self._check(self.lib.armada_round_upload(self.h, C.byref(inp)))
         self._input = inp
 
-    def run(self) -> abi.RoundStats:
+    def run(self, budget_ns: int = 0) -> abi.RoundStats:
+        """`budget_ns` > 0: the cycle's maxSchedulingDuration (scheduling_algo.go:115-118); raises
+        ArmadaError(E_DEADLINE) when it runs out — nothing of the round is committed."""
         stats = abi.RoundStats()
-        self._check(self.lib.armada_round_run(self.h, C.byref(stats)))
+        if budget_ns:
+            self._check(self.lib.armada_round_run_deadline(self.h, C.byref(stats), int(budget_ns)))
+        else:
+            self._check(self.lib.armada_round_run(self.h, C.byref(stats)))
         return stats
 
     def download(self, res: Optional[RoundResult] = None) -> RoundResult:

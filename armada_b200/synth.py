@@ -527,3 +527,21 @@ def rounding_round() -> RawRound:
         static_match=_bitmap([[0]], 1), type_match=_bitmap([[0]], 1),
         job_class=np.zeros(J), job_queue=np.zeros(J), job_submit_time=np.arange(J), queue_weight=np.ones(1),
         indexed=[CPU, MEM], resolution=[17000, 128 * MI], name="rounding")
+
+
+def many_classes_round(seed: int = 9, n_classes: int = 300, n_nodes: int = 80, n_queues: int = 6, n_jobs: int = 1500) -> RawRound:
+    """More distinct scheduling keys than the shared-memory class table holds (256): the table moves
+    to global memory and only the first classes get best-fit windows."""
+    rng = np.random.default_rng(seed)
+    shapes = []
+    c = 0
+    while len(shapes) < n_classes:
+        shapes.append(rl(1 + c % 12, 2 + 2 * (c // 12)))
+        c += 1
+    total = np.repeat(NODE_CPU32[:, None], n_nodes, axis=1)
+    return RawRound(
+        node_total=total, node_allocatable=total.copy(), node_type=np.zeros(n_nodes), node_static_class=np.zeros(n_nodes),
+        class_request=np.stack(shapes), class_pc=np.zeros(n_classes), class_static_row=np.zeros(n_classes),
+        static_match=_bitmap([[0]], 1), type_match=_bitmap([[0]], 1),
+        job_class=rng.integers(0, n_classes, n_jobs), job_queue=rng.integers(0, n_queues, n_jobs), job_submit_time=np.arange(n_jobs),
+        queue_weight=np.ones(n_queues), name=f"many-classes-{n_classes}")

@@ -54,7 +54,10 @@ enum {
   ARMADA_E_CUDA = 3,        /* CUDA runtime error; armada_last_error() has details       */
   ARMADA_E_NO_DEVICE = 4,   /* no CUDA device / library built without kernels           */
   ARMADA_E_INTERNAL = 5,    /* invariant violated (reference would have returned error) */
-  ARMADA_E_STATE = 6        /* call order violated (run before upload, …)               */
+  ARMADA_E_STATE = 6,       /* call order violated (run before upload, …)               */
+  ARMADA_E_DEADLINE = 7     /* armada_round_run_deadline: the time budget ran out; like the reference's
+                               cancelled context (scheduling_algo.go:115-118, queue_scheduler.go:102-107)
+                               nothing of the round is committed: download is refused            */
 };
 
 /* ---- per-job outcome of a round --------------------------------------------------- */
@@ -260,9 +263,9 @@ typedef struct {
 
 /* ---- product entry points (libarmada_b200.so) ------------------------------------- */
 /* Thread safety: one ArmadaRound handle is used by one thread at a time.  Different handles may be
- * used from different threads concurrently, also on the same device: their armada_round_run calls
- * are serialised inside the library (per device), uploads/downloads overlap with a running round
- * of another handle (armada_b200/pools.py pipelines the pools of a cycle this way). */
+ * used from different threads concurrently, also on the same device: up to 8 rounds (pools) run
+ * concurrently on one device — a round is one CTA on one SM — and uploads / downloads overlap with
+ * running rounds of other handles (armada_b200/pools.py schedules the pools of a cycle this way). */
 typedef struct ArmadaRound ArmadaRound;
 
 /* Bind to CUDA device `device` and allocate the per-round context. */
@@ -273,6 +276,12 @@ int32_t armada_round_upload(ArmadaRound* r, const ArmadaRoundInput* in);
 /* Run PreemptingQueueScheduler.Schedule entirely on the device; inputs stay resident so
  * it can be called repeatedly (each call restarts from the uploaded snapshot). */
 int32_t armada_round_run(ArmadaRound* r, ArmadaRoundStats* stats);
+/* The same with a time budget in nanoseconds (0 = none), measured from the call: the reference gives
+ * a scheduling cycle `maxSchedulingDuration` through a context deadline (scheduling_algo.go:115-118)
+ * and the QueueScheduler loop stops when the context is done (queue_scheduler.go:102-107).  The
+ * device checks the budget once per loop iteration; ARMADA_E_DEADLINE leaves the handle as after
+ * armada_round_upload (the round can be run again). */
+int32_t armada_round_run_deadline(ArmadaRound* r, ArmadaRoundStats* stats, uint64_t budget_ns);
 /* Copy results device→host. */
 int32_t armada_round_download(ArmadaRound* r, ArmadaRoundOutput* out);
 int32_t armada_round_destroy(ArmadaRound* r);

@@ -100,6 +100,47 @@ struct NodeDb {
   std::vector<int32_t> sched_prio;       // scheduledAtPriorityByJobId (nodedb.go:140-148)
   std::vector<uint8_t> has_sched_prio;
   std::map<int, uint32_t> evicted_by_index;  // "evictedJobs" table, index "index"
+  // ---- exact acceleration of selectNodeForJobWithFairPreemption (select_fair_preemption_indexed) ----
+  // every node's evicted-table entries (descending walk = reverse iteration), the node each entry sits
+  // on, a log of the nodes whose rows or entries changed, and per (job class, static row) every node's
+  // "trigger index" in an ordered set.  Test infrastructure like the rest of the oracle; checked
+  // against the literal walk by tests/test_golden_units.py (ARMADA_ORACLE_FAIR=check).
+  std::vector<std::set<int>> ev_on_node;
+  std::map<int, uint32_t> ev_node_of_index;
+  std::vector<uint32_t> dirty_log;
+  struct FairIdx {
+    size_t cursor = 0;
+    std::vector<int> trig;
+    std::set<std::pair<int, uint32_t>> order;
+  };
+  std::map<std::pair<uint32_t, uint32_t>, FairIdx> fair_cache;
+  int fair_mode = 0;  // 0 literal below 4096 entries / indexed above, 1 literal, 2 indexed, 3 both + compare
+  void ev_insert(int idx, uint32_t job) {
+    evicted_by_index[idx] = job;
+    const uint32_t n = bound_node[job];
+    if (n != NONE) {
+      if (ev_on_node.size() != N) ev_on_node.assign(N, {});
+      ev_on_node[n].insert(idx);
+      ev_node_of_index[idx] = n;
+      dirty_log.push_back(n);
+    }
+  }
+  void ev_erase(int idx) {
+    evicted_by_index.erase(idx);
+    auto it = ev_node_of_index.find(idx);
+    if (it != ev_node_of_index.end()) {
+      ev_on_node[it->second].erase(idx);
+      dirty_log.push_back(it->second);
+      ev_node_of_index.erase(it);
+    }
+  }
+  void ev_clear() {
+    evicted_by_index.clear();
+    ev_node_of_index.clear();
+    for (auto& s : ev_on_node) s.clear();
+    fair_cache.clear();
+    dirty_log.clear();
+  }
   std::vector<int> evicted_index_of_job;     // "evictedJobs" table, index "id" (-1 = absent)
   std::vector<uint32_t> nodes_by_id;         // node indices in id order ("nodes" table index "id")
   bool in_txn = false;
@@ -107,6 +148,10 @@ struct NodeDb {
   uint64_t stat_probes = 0, stat_fair_scans = 0;
 
   explicit NodeDb(const ArmadaRoundInput* input) : in(input) {
+    if (const char* e = getenv("ARMADA_ORACLE_FAIR")) {
+      std::string m(e);
+      fair_mode = m == "literal" ? 1 : m == "indexed" ? 2 : m == "check" ? 3 : 0;
+    }
     D = (int)in->num_resources;
     R = (int)in->num_indexed;
     PL = (int)in->num_priorities;
@@ -164,6 +209,7 @@ struct NodeDb {
   }
   // UpsertWithTxn, nodedb.go:1148-1159 (re-keys the node in every priority index)
   void upsert(uint32_t n) {
+    dirty_log.push_back(n);
     for (int p = 0; p < PL; ++p) {
       IndexKey nk = make_key(n, p);
       int64_t* ck = &cur_key[((size_t)n * PL + p) * R];
@@ -210,7 +256,7 @@ struct NodeDb {
           evicted_on_node[u.a] = u.flag ? 1 : 0;
           break;
         case Undo::EVTABLE_DEL:
-          evicted_by_index[u.idx] = u.a;
+          ev_insert(u.idx, u.a);
           evicted_index_of_job[u.a] = u.idx;
           break;
       }
@@ -466,9 +512,87 @@ struct NodeDb {
     return NONE;
   }
 
+  // node n's trigger: the evicted-table index at which the reference's descending walk first finds
+  // the node's running total (allocatable at the evicted priority + the evicted jobs seen so far)
+  // large enough — and the node passes the static requirements; -1 = never selected
+  int fair_trigger(uint32_t n, uint32_t row, const int64_t* rq) {
+    if (n >= ev_on_node.size() || ev_on_node[n].empty()) return -1;
+    int lvl_evicted = level_of(EVICTED_PRIORITY);
+    int64_t avail[ARMADA_MAX_RESOURCES];
+    for (int d = 0; d < D; ++d) avail[d] = A(lvl_evicted, d, n);
+    for (auto it = ev_on_node[n].rbegin(); it != ev_on_node[n].rend(); ++it) {
+      const int64_t* erq = req_of(evicted_by_index[*it]);
+      bool dyn = true;
+      for (int d = 0; d < D; ++d) {
+        avail[d] += erq[d];
+        if (rq[d] > avail[d]) dyn = false;
+      }
+      if (dyn) return static_met(n, row, rq) ? *it : -1;
+    }
+    return -1;
+  }
+  // The same selection as the literal walk below without re-walking the table: the walk reaches the
+  // node with the LARGEST trigger index first.
+  uint32_t select_fair_preemption_indexed(JobCtx& jc, bool commit) {
+    const int64_t* rq = req_of(jc.job);
+    auto key = std::make_pair(in->job_class[jc.job], jc.row);
+    auto ins = fair_cache.try_emplace(key);
+    FairIdx& F = ins.first->second;
+    auto recompute = [&](uint32_t n) {
+      int old = F.trig[n];
+      int t = fair_trigger(n, jc.row, rq);
+      if (old == t) return;
+      if (old >= 0) F.order.erase({old, n});
+      if (t >= 0) F.order.insert({t, n});
+      F.trig[n] = t;
+    };
+    if (ins.second) {
+      F.trig.assign(N, -1);
+      for (uint32_t n = 0; n < (uint32_t)ev_on_node.size(); ++n)
+        if (!ev_on_node[n].empty()) recompute(n);
+      F.cursor = dirty_log.size();
+    } else {
+      for (; F.cursor < dirty_log.size(); ++F.cursor) recompute(dirty_log[F.cursor]);
+    }
+    if (F.order.empty()) return NONE;
+    const int trig = F.order.rbegin()->first;
+    const uint32_t n = F.order.rbegin()->second;
+    if (!commit) return n;
+    std::vector<std::pair<int, uint32_t>> victims;
+    for (auto it = ev_on_node[n].rbegin(); it != ev_on_node[n].rend() && *it >= trig; ++it) victims.emplace_back(*it, evicted_by_index[*it]);
+    int32_t max_priority = MIN_PRIORITY;
+    for (auto& [eidx, pj] : victims) {
+      unbind(pj, n);
+      if (in_txn) {
+        Undo u;
+        u.kind = Undo::EVTABLE_DEL;
+        u.a = pj;
+        u.idx = eidx;
+        undo.push_back(u);
+      }
+      ev_erase(eidx);
+      evicted_index_of_job[pj] = -1;
+      int32_t pr = has_sched_prio[pj] ? sched_prio[pj] : pc_of(pj).priority;
+      if (pr > max_priority) max_priority = pr;
+    }
+    jc.p_node = n;
+    jc.p_preempted_at = max_priority;
+    return n;
+  }
+
   // selectNodeForJobWithFairPreemption, nodedb.go:812-903
   uint32_t select_fair_preemption(JobCtx& jc) {
     ++stat_fair_scans;
+    if (fair_mode == 2 || (fair_mode == 0 && evicted_by_index.size() >= 4096)) return select_fair_preemption_indexed(jc, true);
+    if (fair_mode == 3) {
+      const uint32_t want = select_fair_preemption_indexed(jc, false);
+      const uint32_t got = select_fair_preemption_literal(jc);
+      if (want != got) fail(ARMADA_E_INTERNAL, "indexed fair preemption disagrees with the literal walk");
+      return got;
+    }
+    return select_fair_preemption_literal(jc);
+  }
+  uint32_t select_fair_preemption_literal(JobCtx& jc) {
     struct Considered {
       std::vector<int64_t> avail;
       std::vector<std::pair<int, uint32_t>> evicted;  // (index, job)
@@ -514,7 +638,7 @@ struct NodeDb {
           u.idx = eidx;
           undo.push_back(u);
         }
-        evicted_by_index.erase(eidx);
+        ev_erase(eidx);
         evicted_index_of_job[pj] = -1;
         int32_t pr = has_sched_prio[pj] ? sched_prio[pj] : pc_of(pj).priority;
         if (pr > max_priority) max_priority = pr;
@@ -641,7 +765,7 @@ struct NodeDb {
           u.idx = idx;
           undo.push_back(u);
         }
-        evicted_by_index.erase(idx);
+        ev_erase(idx);
         evicted_index_of_job[jc->job] = -1;
       }
     }
@@ -1337,7 +1461,7 @@ struct Round {
     for (auto& v : repo)
       std::sort(v.begin(), v.end(), [&](JobCtx* a, JobCtx* b) { return order_less(a->job, b->job); });
     // nodeDb.Reset :260-274
-    db.evicted_by_index.clear();
+    db.ev_clear();
     std::fill(db.evicted_index_of_job.begin(), db.evicted_index_of_job.end(), -1);
     add_evicted_jobs_to_nodedb(repo);
     return res;
@@ -1361,7 +1485,7 @@ struct Round {
       Gang& g = ci.items[(size_t)top].it->next;
       for (JobCtx* jc : g.jctxs) {
         if (db.evicted_index_of_job[jc->job] >= 0) fail(ARMADA_E_INTERNAL, "tried to insert evicted job with duplicate index");
-        db.evicted_by_index[i] = jc->job;
+        db.ev_insert(i, jc->job);
         db.evicted_index_of_job[jc->job] = i;
         ++i;
       }
@@ -1703,7 +1827,7 @@ int32_t armada_oracle_nodedb_add_evicted(ArmadaOracleNodeDb* h, uint32_t job, in
     if (index >= 0) {
       if (h->db.evicted_index_of_job[job] >= 0 || h->db.evicted_by_index.count(index))
         fail(ARMADA_E_INVALID, "duplicate evicted index");
-      h->db.evicted_by_index[index] = job;
+      h->db.ev_insert(index, job);
       h->db.evicted_index_of_job[job] = index;
     }
   });

@@ -64,3 +64,4 @@ def test_product_fails_loudly_without_a_device():
     with pytest.raises(abi.ArmadaError) as ei:
         DeviceRound(0)
     assert ei.value.status in (abi.E_NO_DEVICE, abi.E_CUDA)
+

@@ -205,3 +205,28 @@ def test_exact_mode_forced_on_aligned_rounds(seed):
         dev.close()
     finally:
         os.environ.pop("ARMADA_FORCE_EXACT", None)
+
+
+def test_more_classes_than_the_shared_memory_table_holds():
+    r = synth.many_classes_round()
+    got, _ = assert_parity(r.to_input(), r.name)
+    assert got.out.num_result_scheduled > 0
+
+
+def test_time_budget_aborts_the_round_and_leaves_the_snapshot_runnable():
+    """armada_round_run_deadline: a budget that cannot be met returns ARMADA_E_DEADLINE (the reference's
+    cancelled context, scheduling_algo.go:115-118), download is refused, and the same handle still
+    schedules the uploaded snapshot afterwards — bit-exact.  (Emulated kernel build: no GPU needed.)"""
+    r = synth.random_round(3, n_nodes=50, n_jobs=300, n_running=60)
+    inp = r.to_input()
+    dev = emu_lib.emu_round()
+    dev.upload(inp)
+    with pytest.raises(abi.ArmadaError) as ei:
+        dev.run(budget_ns=1)
+    assert ei.value.status == abi.E_DEADLINE
+    with pytest.raises(abi.ArmadaError) as ei:
+        dev.download()
+    assert ei.value.status == abi.E_STATE
+    dev.run(budget_ns=60_000_000_000)
+    assert not dev.download().diff(oracle_lib.round_schedule(inp))
+    dev.close()
