@@ -195,6 +195,12 @@ def declare_prototypes(lib: C.CDLL) -> None:
     lib.armada_round_destroy.restype = C.c_int32
     lib.armada_round_schedule.argtypes = [vp, C.POINTER(RoundInput), C.POINTER(RoundOutput), C.POINTER(RoundStats)]
     lib.armada_round_schedule.restype = C.c_int32
+    lib.armada_nodedb_create.argtypes = [C.c_int32, C.POINTER(RoundInput), C.POINTER(vp)]
+    lib.armada_nodedb_create.restype = C.c_int32
+    lib.armada_nodedb_schedule_many.argtypes = [vp, C.c_uint32, u32p, u32p, u8p, u32p]
+    lib.armada_nodedb_schedule_many.restype = C.c_int32
+    lib.armada_nodedb_destroy.argtypes = [vp]
+    lib.armada_nodedb_destroy.restype = C.c_int32
     lib.armada_strerror.argtypes = [C.c_int32]
     lib.armada_strerror.restype = C.c_char_p
     lib.armada_last_error.argtypes = []
@@ -226,6 +232,9 @@ PRODUCT_SYMBOLS = [
     "armada_round_download",
     "armada_round_destroy",
     "armada_round_schedule",
+    "armada_nodedb_create",
+    "armada_nodedb_schedule_many",
+    "armada_nodedb_destroy",
     "armada_strerror",
     "armada_last_error",
     "armada_abi_version",

@@ -480,6 +480,43 @@ __global__ void k_xkeys(DevCfg c, DevPtrs P) {
   P.xkey[i] = key;
 }
 
+// Snapshot construction on the device (calculateJobSchedulingInfo + constructSchedulingContext,
+// scheduling_algo.go:522-632,664-676) when the caller leaves the queue accounting to the library:
+// segmented sums over the job SoA — allocation per (queue, priority class) over the running jobs,
+// demand over every job (running jobs only for a cordoned queue) — then the demand capped at the
+// per-queue per-class limit (constraints.go:187-197) and summed over the classes.
+__global__ void k_snapshot_jobs(DevCfg c, DevPtrs P, int64_t* alloc_pc, int64_t* demand_pc, int want_alloc) {
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= c.J) return;
+  const uint32_t q = P.job_queue[j];
+  if (q == NONE) return;
+  const uint32_t cls = P.job_class[j];
+  const uint32_t pc = P.class_pc[cls];
+  const bool running = P.job_node0[j] != NONE;
+  const bool cordoned = P.queue_cordoned[q] != 0;
+  for (int d = 0; d < c.D; ++d) {
+    const int64_t r = P.class_req_raw[(size_t)cls * c.D + d];
+    if (!r) continue;
+    if (running && want_alloc) atomic_add_i64(&alloc_pc[((size_t)q * c.PC + pc) * c.D + d], r);
+    if (running || !cordoned) atomic_add_i64(&demand_pc[((size_t)q * c.PC + pc) * c.D + d], r);
+  }
+}
+__global__ void k_snapshot_queues(DevCfg c, DevPtrs P, const int64_t* demand_pc, int64_t* cdemand) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.Q * c.D) return;
+  const int q = i / c.D, d = i - q * c.D;
+  int64_t sum = 0;
+  for (int pc = 0; pc < c.PC; ++pc) {
+    int64_t v = demand_pc[((size_t)q * c.PC + pc) * c.D + d];
+    if (P.queue_has_limit[(size_t)q * c.PC + pc]) {
+      const int64_t lim = P.queue_limit[((size_t)q * c.PC + pc) * c.D + d];
+      if (lim < v) v = lim;
+    }
+    sum += v;
+  }
+  cdemand[i] = sum;
+}
+
 // static class of the node at every G0 position
 __global__ void k_g0_sc(DevCfg c, DevPtrs P) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -576,4 +613,5 @@ __global__ void k_finalize(DevCfg c, DevPtrs P, uint8_t* out_state, uint32_t* ou
 
 }  // namespace
 
+#include "armada_dryrun.inc"
 #include "armada_host.inc"

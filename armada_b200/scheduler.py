@@ -91,3 +91,43 @@ class PreemptingQueueScheduler:
 
 def round_schedule(inp: abi.RoundInput, device: int = 0) -> RoundResult:
     return PreemptingQueueScheduler(inp, device).schedule()
+
+
+class DeviceNodeDb:
+    """`NodeDb` on an empty cluster for dry-run gang checks — what SubmitChecker builds per executor
+    (internal/scheduler/submitcheck.go:302-422).  `schedule_many(gangs)` = one
+    `ScheduleManyWithTxn` + `Abort` per gang (gangs are lists of job-class indices), all gangs of the
+    call in one kernel launch."""
+
+    def __init__(self, inp: abi.RoundInput, device: int = 0, lib=None):
+        self.lib = lib if lib is not None else abi.load_product()
+        self.h = C.c_void_p()
+        self._input = inp
+        st = self.lib.armada_nodedb_create(device, C.byref(inp), C.byref(self.h))
+        if st != abi.OK:
+            raise abi.ArmadaError(st, f"{self.lib.armada_strerror(st).decode()}: {self.lib.armada_last_error().decode()}")
+
+    def schedule_many(self, gangs):
+        import numpy as np
+        start = np.zeros(len(gangs) + 1, np.uint32)
+        start[1:] = np.cumsum([len(g) for g in gangs])
+        members = np.asarray([c for g in gangs for c in g] or [0], dtype=np.uint32)
+        ok = np.zeros(max(len(gangs), 1), np.uint8)
+        node = np.full(max(int(start[-1]), 1), abi.NONE, np.uint32)
+        st = self.lib.armada_nodedb_schedule_many(self.h, len(gangs), start.ctypes.data_as(abi.u32p), members.ctypes.data_as(abi.u32p),
+                                                  ok.ctypes.data_as(abi.u8p), node.ctypes.data_as(abi.u32p))
+        if st != abi.OK:
+            raise abi.ArmadaError(st, f"{self.lib.armada_strerror(st).decode()}: {self.lib.armada_last_error().decode()}")
+        out_nodes = [node[int(start[g]):int(start[g + 1])].copy() for g in range(len(gangs))]
+        return ok[: len(gangs)].astype(bool), out_nodes
+
+    def close(self):
+        if self.h:
+            self.lib.armada_nodedb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

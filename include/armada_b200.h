@@ -194,6 +194,11 @@ typedef struct {
   uint32_t num_queues;                                 /* Q */
   const double* queue_weight;        /* [Q] 1/priorityFactor                                  */
   const uint8_t* queue_cordoned;     /* [Q] */
+  /* The next three may be NULL: the library then builds this part of the snapshot itself from the job
+   * arrays (calculateJobSchedulingInfo + constructSchedulingContext, scheduling_algo.go:522-632,
+   * 664-676) — allocation = running jobs per queue and priority class, demand = every job (running
+   * jobs only for a cordoned queue), constrained demand = the per-class demand capped at queue_limit
+   * (constraints.go:187-197) — on the device (k_snapshot_jobs / k_snapshot_queues). */
   const int64_t* queue_allocated_by_pc; /* [Q][PC][D] initial AllocatedByPriorityClass         */
   const int64_t* queue_demand;          /* [Q][D]  (informational)                             */
   const int64_t* queue_constrained_demand; /* [Q][D] drives fair shares, scheduling.go:252-332 */
@@ -288,6 +293,27 @@ int32_t armada_round_destroy(ArmadaRound* r);
 /* One-call form with host buffers on both sides: upload + run + download. */
 int32_t armada_round_schedule(ArmadaRound* r, const ArmadaRoundInput* in, ArmadaRoundOutput* out,
                               ArmadaRoundStats* stats);
+/* ---- dry-run NodeDb (SubmitChecker) ---------------------------------------------------------------
+ * internal/scheduler/submitcheck.go:302-422 checks every newly submitted job / gang against an EMPTY
+ * copy of each executor's nodes: NodeDb.ScheduleManyWithTxn (nodedb.go:386-418) inside a transaction
+ * that is always aborted (submitcheck.go:372-380).  The checks are independent of each other, so a
+ * batch of them is one kernel launch: one thread block per gang walks the reference's ordered node
+ * iterators literally (rounded index keys, unrounded acceptance, per-node-type streams merged on the
+ * unrounded quantities — the same code path as the round's exact mode) over the cluster's rows plus
+ * the gang's own placements so far. */
+typedef struct ArmadaNodeDb ArmadaNodeDb;
+/* Nodes, node types, index configuration, priority classes and job classes are read from `in`
+ * (NewNodeDb + CreateAndInsertWithJobDbJobsWithTxn with no jobs, submitcheck.go:318-340); its jobs and
+ * queues are ignored. */
+int32_t armada_nodedb_create(int32_t device, const ArmadaRoundInput* in, ArmadaNodeDb** out);
+/* num_gangs gangs in CSR form: gang g = member_class[gang_start[g] .. gang_start[g+1]), each member
+ * a job-class index of `in` (its scheduling key).  ok[g] = 1 when every member found a node;
+ * member_node (optional, [gang_start[num_gangs]]) = the node each member of a schedulable gang was
+ * placed on (caller's node numbering), ARMADA_NONE for the members of the others. */
+int32_t armada_nodedb_schedule_many(ArmadaNodeDb* db, uint32_t num_gangs, const uint32_t* gang_start, const uint32_t* member_class,
+                                    uint8_t* ok, uint32_t* member_node);
+int32_t armada_nodedb_destroy(ArmadaNodeDb* db);
+
 const char* armada_strerror(int32_t status);
 const char* armada_last_error(void);
 uint32_t armada_abi_version(void);

@@ -858,8 +858,45 @@ struct Round {
   const int64_t* req_of(uint32_t job) const { return db.req_of(job); }
   uint32_t pc_index(uint32_t job) const { return in->class_pc[in->job_class[job]]; }
 
+  // Snapshot construction when the caller leaves the queue accounting to the library (NULL
+  // queue_allocated_by_pc / queue_constrained_demand): calculateJobSchedulingInfo
+  // (scheduling_algo.go:522-632: allocation = running jobs per queue and priority class, demand = every
+  // job of the pool, running jobs only for a cordoned queue) and constructSchedulingContext (:664-676:
+  // constrained demand = the per-priority-class demand capped at the per-queue limit,
+  // constraints.go:187-197, summed over the classes).
+  std::vector<int64_t> der_alloc_pc, der_cdemand;
+  void derive_snapshot() {
+    der_alloc_pc.assign((size_t)Q * PC * D, 0);
+    std::vector<int64_t> demand_pc((size_t)Q * PC * D, 0);
+    for (uint32_t j = 0; j < J; ++j) {
+      uint32_t q = in->job_queue[j];
+      if (q == NONE) continue;
+      const uint32_t cls = in->job_class[j];
+      const uint32_t pc = in->class_pc[cls];
+      const bool running = in->job_node[j] != NONE;
+      const bool cordoned = in->queue_cordoned && in->queue_cordoned[q];
+      for (int d = 0; d < D; ++d) {
+        const int64_t r = in->class_request[(size_t)cls * D + d];
+        if (running) der_alloc_pc[((size_t)q * PC + pc) * D + d] += r;
+        if (running || !cordoned) demand_pc[((size_t)q * PC + pc) * D + d] += r;
+      }
+    }
+    der_cdemand.assign((size_t)Q * D, 0);
+    for (uint32_t q = 0; q < Q; ++q)
+      for (int pc = 0; pc < PC; ++pc)
+        for (int d = 0; d < D; ++d) {
+          int64_t v = demand_pc[((size_t)q * PC + pc) * D + d];
+          if (in->queue_has_limit && in->queue_has_limit[(size_t)q * PC + pc] && in->queue_limit) {
+            const int64_t lim = in->queue_limit[((size_t)q * PC + pc) * D + d];
+            if (lim < v) v = lim;
+          }
+          der_cdemand[(size_t)q * D + d] += v;
+        }
+  }
+
   // AddQueueSchedulingContext (scheduling.go:104-156) + UpdateFairShares (:174-182)
   void build_queue_contexts() {
+    if (!in->queue_allocated_by_pc || !in->queue_constrained_demand) derive_snapshot();
     qctx.resize(Q);
     for (uint32_t q = 0; q < Q; ++q) {
       QueueCtx& c = qctx[q];
@@ -869,7 +906,7 @@ struct Round {
       c.penalty.assign(D, 0);
       for (int pc = 0; pc < PC; ++pc)
         for (int d = 0; d < D; ++d) {
-          int64_t v = in->queue_allocated_by_pc ? in->queue_allocated_by_pc[((size_t)q * PC + pc) * D + d] : 0;
+          int64_t v = in->queue_allocated_by_pc ? in->queue_allocated_by_pc[((size_t)q * PC + pc) * D + d] : der_alloc_pc[((size_t)q * PC + pc) * D + d];
           c.allocated_by_pc[(size_t)pc * D + d] = v;
           c.allocated[d] += v;
         }
@@ -901,8 +938,8 @@ struct Round {
       double cds = 1.0;
       if (!total_all_zero) {
         std::vector<int64_t> cd(D, 0);
-        if (in->queue_constrained_demand)
-          for (int d = 0; d < D; ++d) cd[d] = in->queue_constrained_demand[(size_t)q * D + d];
+        for (int d = 0; d < D; ++d)
+          cd[d] = in->queue_constrained_demand ? in->queue_constrained_demand[(size_t)q * D + d] : der_cdemand[(size_t)q * D + d];
         cds = unweighted_cost(cd.data());
       }
       qi[q].cds = cds;
@@ -1794,6 +1831,27 @@ int32_t armada_oracle_nodedb_schedule_many(ArmadaOracleNodeDb* h, const uint32_t
       if (preempted_at) preempted_at[i] = jc.has_pctx ? jc.p_preempted_at : ARMADA_NO_PRIORITY;
       if (method) method[i] = jc.has_pctx ? jc.p_method : (uint8_t)ARMADA_METHOD_NONE;
     }
+  });
+}
+
+// The same inside a transaction that is always aborted: what SubmitChecker does per gang and
+// executor (internal/scheduler/submitcheck.go:372-380) — the NodeDb is unchanged afterwards.
+int32_t armada_oracle_nodedb_dry_run(ArmadaOracleNodeDb* h, const uint32_t* jobs, uint32_t n, uint8_t* ok, uint32_t* node) {
+  ORACLE_GUARD({
+    std::vector<JobCtx*> gang;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (jobs[i] >= h->db.J) fail(ARMADA_E_INVALID, "job out of range");
+      JobCtx& jc = h->jctx[jobs[i]];
+      jc.has_pctx = false;
+      jc.p_node = NONE;
+      gang.push_back(&jc);
+    }
+    h->db.begin();
+    bool all = h->db.schedule_many(gang);
+    h->db.abort();
+    if (ok) *ok = all ? 1 : 0;
+    for (uint32_t i = 0; i < n; ++i)
+      if (node) node[i] = (all && gang[i]->has_pctx) ? gang[i]->p_node : NONE;
   });
 }
 

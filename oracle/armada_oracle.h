@@ -46,6 +46,9 @@ int32_t armada_oracle_nodedb_schedule_many(ArmadaOracleNodeDb* db, const uint32_
 /* EvictJobsFromNode / UnbindJobFromNode + Upsert (nodedb.go:960-1003,1039-1098). */
 int32_t armada_oracle_nodedb_evict(ArmadaOracleNodeDb* db, uint32_t job);
 int32_t armada_oracle_nodedb_unbind(ArmadaOracleNodeDb* db, uint32_t job);
+/* ScheduleManyWithTxn inside a transaction that is always aborted (SubmitChecker,
+ * submitcheck.go:372-380): the NodeDb is unchanged afterwards. */
+int32_t armada_oracle_nodedb_dry_run(ArmadaOracleNodeDb* db, const uint32_t* jobs, uint32_t n, uint8_t* ok, uint32_t* node);
 /* Mark an evicted job as pinned to its node for re-scheduling (jctx.SetAssignedNode,
  * eviction.go:245-252) and register it for fair preemption
  * (AddEvictedJobSchedulingContextWithTxn, nodedb.go:1193-1203). */

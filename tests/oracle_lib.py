@@ -52,6 +52,8 @@ def load() -> C.CDLL:
     lib.armada_oracle_nodedb_destroy.restype = None
     lib.armada_oracle_nodedb_schedule_many.argtypes = [vp, abi.u32p, C.c_uint32, abi.u8p, abi.u32p, abi.i32p, abi.i32p, abi.u8p]
     lib.armada_oracle_nodedb_schedule_many.restype = C.c_int32
+    lib.armada_oracle_nodedb_dry_run.argtypes = [vp, abi.u32p, C.c_uint32, abi.u8p, abi.u32p]
+    lib.armada_oracle_nodedb_dry_run.restype = C.c_int32
     lib.armada_oracle_nodedb_evict.argtypes = [vp, C.c_uint32]
     lib.armada_oracle_nodedb_evict.restype = C.c_int32
     lib.armada_oracle_nodedb_unbind.argtypes = [vp, C.c_uint32]
@@ -112,6 +114,15 @@ class OracleNodeDb:
             self.h, ja.ctypes.data_as(abi.u32p), n, C.byref(ok), node.ctypes.data_as(abi.u32p),
             sa.ctypes.data_as(abi.i32p), pa.ctypes.data_as(abi.i32p), me.ctypes.data_as(abi.u8p)))
         return bool(ok.value), node, sa, pa, me
+
+    def dry_run(self, jobs):
+        """ScheduleManyWithTxn + Abort (what SubmitChecker does): (ok, nodes)"""
+        n = len(jobs)
+        ja = np.asarray(jobs, dtype=np.uint32)
+        ok = C.c_uint8(0)
+        node = np.full(n, abi.NONE, np.uint32)
+        check(self.lib.armada_oracle_nodedb_dry_run(self.h, ja.ctypes.data_as(abi.u32p), n, C.byref(ok), node.ctypes.data_as(abi.u32p)))
+        return bool(ok.value), node
 
     def evict(self, job):
         check(self.lib.armada_oracle_nodedb_evict(self.h, job))

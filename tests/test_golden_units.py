@@ -234,3 +234,65 @@ def test_eviction_allocatable_vectors():
     db.unbind(1)
     a = db.get_alloc(0)
     assert all((a[lvl] == vec(32, 256)).all() for lvl in range(len(prios)))
+
+
+# ---- TestScheduleIndividually / TestScheduleMany (nodedb/nodedb_test.go:424-588, :590-670) --------
+SCHED_ONE = gt.load_cases("schedule_individually")
+SCHED_MANY = gt.load_cases("schedule_many")
+
+
+def _nodedb_for(nodes, job_groups, env):
+    cfg = fx.test_scheduling_config()
+    jobs = [j for g in job_groups for j in g]
+    t = 0
+    for j in jobs:
+        t += 1
+        j.submit_time = t
+    queues = sorted({j.queue for j in jobs})
+    b = RoundInputBuilder(cfg, nodes, jobs, [QueueSpec(q, 1.0) for q in queues])
+    return b, oracle_lib.OracleNodeDb(b.input)
+
+
+@pytest.mark.parametrize("name", sorted(SCHED_ONE.keys()))
+def test_schedule_individually(name):
+    """One ScheduleManyWithTxn call per job on the same NodeDb, committed when it succeeds."""
+    env = gt.Env()
+    try:
+        tc = env.ev(SCHED_ONE[name])
+    except gt.UnsupportedCase as e:
+        pytest.skip(f"not modelled: {e}")
+    jobs = tc["Jobs"]
+    for j in jobs:
+        j.gang_id, j.gang_cardinality = None, 1
+    b, db = _nodedb_for(tc["Nodes"], [[j] for j in jobs], env)
+    want = [bool(x) for x in tc["ExpectSuccess"]]
+    got = []
+    for j in jobs:
+        ok, node, _, _, _ = db.schedule_many([b.job_pos[j.id]])
+        got.append(ok)
+        if ok:
+            assert node[0] != abi.NONE
+    assert got == want
+
+
+@pytest.mark.parametrize("name", sorted(SCHED_MANY.keys()))
+def test_schedule_many(name):
+    """Gang transactions: all members or none (the failed gang leaves no trace: "correct rollback")."""
+    env = gt.Env()
+    # locals of the reference's test function (nodedb_test.go:591-592); fresh job objects per use
+    env.ids["gangSuccess"] = gt._Fresh(lambda: fx.with_gang(env.fx.n_1cpu_4gi("A", fx.PriorityClass0, 32)))
+    env.ids["gangFailure"] = gt._Fresh(lambda: fx.with_gang(env.fx.n_1cpu_4gi("A", fx.PriorityClass0, 33)))
+    try:
+        tc = env.ev(SCHED_MANY[name])
+    except gt.UnsupportedCase as e:
+        pytest.skip(f"not modelled: {e}")
+    groups = tc["Jobs"]
+    b, db = _nodedb_for(tc["Nodes"], groups, env)
+    want = [bool(x) for x in tc["ExpectSuccess"]]
+    got = []
+    for g in groups:
+        ok, node, _, _, _ = db.schedule_many([b.job_pos[j.id] for j in g])
+        got.append(ok)
+        if ok:
+            assert (node != abi.NONE).all()
+    assert got == want

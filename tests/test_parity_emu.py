@@ -6,6 +6,8 @@ data-structure bugs in the kernels are caught on a CPU-only box.  EMU_ORDER=reve
 lanes of every warp in the opposite order (catches missing __syncwarp in either direction)."""
 import os
 
+import numpy as np
+
 import pytest
 
 import emu_lib
@@ -230,3 +232,74 @@ def test_time_budget_aborts_the_round_and_leaves_the_snapshot_runnable():
     dev.run(budget_ns=60_000_000_000)
     assert not dev.download().diff(oracle_lib.round_schedule(inp))
     dev.close()
+
+
+def _dry_run_case(r, gangs_as_jobs, lib):
+    """gangs_as_jobs: lists of job indices; the product takes the jobs' classes."""
+    from armada_b200.scheduler import DeviceNodeDb
+    inp = r.to_input()
+    jc = np.asarray(r.job_class).astype(np.int64)
+    odb = oracle_lib.OracleNodeDb(inp)
+    want_ok, want_nodes = [], []
+    for g in gangs_as_jobs:
+        ok, nodes = odb.dry_run(g)
+        want_ok.append(ok)
+        want_nodes.append(nodes)
+    with DeviceNodeDb(inp, 0, lib=lib) as db:
+        got_ok, got_nodes = db.schedule_many([[int(jc[j]) for j in g] for g in gangs_as_jobs])
+    assert list(got_ok) == want_ok
+    for g, (a, b) in enumerate(zip(got_nodes, want_nodes)):
+        assert (a == b).all(), f"gang {g}: {a} vs {b}"
+    return want_ok
+
+
+@pytest.mark.parametrize("seed,unaligned", [(0, False), (1, True), (2, True), (3, False)])
+def test_dry_run_nodedb_matches_the_oracle(seed, unaligned):
+    """armada_nodedb_schedule_many (SubmitChecker's ScheduleManyWithTxn + Abort on an empty cluster,
+    submitcheck.go:302-422): single jobs and gangs of every class, including gangs too big for the
+    cluster, against the oracle's NodeDb — same verdicts, same nodes."""
+    r = synth.random_round(seed, n_nodes=30 + 7 * seed, n_jobs=200, n_running=0, gangs=False, unaligned=unaligned, away=(seed == 1))
+    rng = np.random.default_rng(seed)
+    J = len(np.asarray(r.job_class))
+    gangs = [[int(j)] for j in rng.choice(J, 40, replace=False)]
+    for _ in range(12):
+        size = int(rng.integers(2, 150))
+        j0 = int(rng.integers(0, J))
+        cls = np.asarray(r.job_class)[j0]
+        same = np.nonzero(np.asarray(r.job_class) == cls)[0]
+        gangs.append([int(same[i % len(same)]) for i in range(size)] if len(same) >= 1 else [j0])
+    # the oracle's jobs must be distinct inside one gang
+    gangs = [list(dict.fromkeys(g)) for g in gangs]
+    oks = _dry_run_case(r, gangs, emu_lib.load())
+    assert any(oks)
+
+
+def test_dry_run_nodedb_resolution_rounding():
+    """The rounded index key can hide a node from the iterator even on an empty cluster: 20 cpu on a
+    32-cpu node with a 17-cpu index resolution (rounded 17 < 20) is unschedulable in the reference."""
+    r = synth.rounding_round()
+    r.class_request = np.stack([synth.rl(16, 128), synth.rl(20, 128)])
+    r.class_pc = np.zeros(2)
+    r.class_static_row = np.zeros(2)
+    r.job_class = np.array([0, 0, 1, 1])
+    oks = _dry_run_case(r, [[0], [2], [0, 1], [3]], emu_lib.load())
+    assert oks == [True, False, True, False]
+
+
+@pytest.mark.parametrize("seed", [2, 4, 10])
+def test_snapshot_construction_on_the_device(seed):
+    """NULL queue_allocated_by_pc / queue_constrained_demand: the library derives the queue accounting
+    from the job arrays (calculateJobSchedulingInfo + constructSchedulingContext,
+    scheduling_algo.go:522-632,664-676) — on the device in the product (k_snapshot_*), restated in the
+    oracle; without per-queue limits that equals what the host-side generator passes explicitly."""
+    limits = seed == 4
+    r = synth.random_round(seed, n_nodes=50, n_jobs=350, n_running=100, protected_fraction=0.5, queue_limits=limits)
+    inp = r.to_input()
+    explicit = oracle_lib.round_schedule(inp)
+    inp.queue_allocated_by_pc = None
+    inp.queue_constrained_demand = None
+    want = oracle_lib.round_schedule(inp)
+    got = emu_round(inp)
+    assert not got.diff(want)
+    if not limits:
+        assert not want.diff(explicit)

@@ -222,3 +222,48 @@ def test_full_size_properties():
     qa = np.zeros_like(a.queue_allocated)
     np.add.at(qa, np.asarray(r.job_queue).astype(np.int64)[sched], req[sched])
     assert (qa == a.queue_allocated).all()
+
+
+def _dry_run_case(r, gangs_as_jobs):
+    from armada_b200.scheduler import DeviceNodeDb
+    inp = r.to_input()
+    jc = np.asarray(r.job_class).astype(np.int64)
+    odb = oracle_lib.OracleNodeDb(inp)
+    want = [odb.dry_run(g) for g in gangs_as_jobs]
+    with DeviceNodeDb(inp, 0) as db:
+        got_ok, got_nodes = db.schedule_many([[int(jc[j]) for j in g] for g in gangs_as_jobs])
+    assert list(got_ok) == [w[0] for w in want]
+    for g, (a, w) in enumerate(zip(got_nodes, want)):
+        assert (a == w[1]).all(), f"gang {g}: {a} vs {w[1]}"
+    return [w[0] for w in want]
+
+
+@pytest.mark.parametrize("seed,unaligned,n_nodes", [(0, False, 60), (1, True, 80), (2, True, 2500), (3, False, 5000)])
+def test_dry_run_nodedb_matches_the_oracle(seed, unaligned, n_nodes):
+    """armada_nodedb_schedule_many — SubmitChecker's ScheduleManyWithTxn + Abort on an empty cluster
+    (submitcheck.go:302-422) — for a batch of single jobs and gangs in one launch: the oracle's
+    verdicts and nodes."""
+    r = synth.random_round(seed, n_nodes=n_nodes, n_jobs=400, n_running=0, gangs=False, unaligned=unaligned, away=(seed == 1))
+    rng = np.random.default_rng(seed)
+    J = len(np.asarray(r.job_class))
+    gangs = [[int(j)] for j in rng.choice(J, 120, replace=False)]
+    for _ in range(30):
+        size = int(rng.integers(2, 200))
+        cls = np.asarray(r.job_class)[int(rng.integers(0, J))]
+        same = np.nonzero(np.asarray(r.job_class) == cls)[0]
+        gangs.append(list(dict.fromkeys(int(same[i % len(same)]) for i in range(size))))
+    assert any(_dry_run_case(r, gangs))
+
+
+def test_dry_run_nodedb_resolution_rounding():
+    r = synth.rounding_round()
+    r.class_request = np.stack([synth.rl(16, 128), synth.rl(20, 128)])
+    r.class_pc = np.zeros(2)
+    r.class_static_row = np.zeros(2)
+    r.job_class = np.array([0, 0, 1, 1])
+    assert _dry_run_case(r, [[0], [2], [0, 1], [3]]) == [True, False, True, False]
+
+
+def test_more_classes_than_the_shared_memory_table_holds():
+    r = synth.many_classes_round(n_nodes=600, n_jobs=12000)
+    assert_parity(r.to_input(), r.name)
