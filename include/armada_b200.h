@@ -49,8 +49,10 @@ extern "C" {
 enum {
   ARMADA_OK = 0,
   ARMADA_E_INVALID = 1,     /* malformed input (bad sizes, ids out of range, NULL)      */
-  ARMADA_E_UNSUPPORTED = 2, /* valid input outside the device fast-path domain; nothing
-                               was computed (see DESIGN.md "supported domain")          */
+  ARMADA_E_UNSUPPORTED = 2, /* valid input the device path does not cover (more than 128 queues, a
+                               best-fit key wider than 63 bits, … — DESIGN.md §4); nothing was computed.
+                               Quantities never cause it: unaligned / oddly ordered inputs run in
+                               exact mode                                                */
   ARMADA_E_CUDA = 3,        /* CUDA runtime error; armada_last_error() has details       */
   ARMADA_E_NO_DEVICE = 4,   /* no CUDA device / library built without kernels           */
   ARMADA_E_INTERNAL = 5,    /* invariant violated (reference would have returned error) */
@@ -263,14 +265,15 @@ typedef struct {
                                     batches, 7 pipeline epilogue.  phase_cycles[4] = iterations run in
                                     batch mode */
   uint64_t batch_debug[8];       /* device only: 0 assignment loop busy cycles, 1 assignment loop cycles
-                                    waiting for records, 2 pipeline runs, 3 batches cut short, 4.. spare */
+                                    waiting for records, 2 pipeline runs, 3 batches cut short, 6 candidate
+                                    refills from the sorted index, 7 cycles spent in them; 4, 5 spare */
 } ArmadaRoundStats;
 
 /* ---- product entry points (libarmada_b200.so) ------------------------------------- */
 /* Thread safety: one ArmadaRound handle is used by one thread at a time.  Different handles may be
- * used from different threads concurrently, also on the same device: up to 8 rounds (pools) run
- * concurrently on one device — a round is one CTA on one SM — and uploads / downloads overlap with
- * running rounds of other handles (armada_b200/pools.py schedules the pools of a cycle this way). */
+ * used from different threads concurrently, also on the same device: rounds (pools) run concurrently
+ * there — a round is one CTA on one SM — and uploads / downloads overlap with running rounds of
+ * other handles (armada_b200/pools.py schedules the pools of a cycle this way). */
 typedef struct ArmadaRound ArmadaRound;
 
 /* Bind to CUDA device `device` and allocate the per-round context. */
