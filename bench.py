@@ -34,6 +34,10 @@ import sys
 import threading
 import time
 
+# Before anything creates the CUDA context: one hardware work queue per concurrent round (the pools
+# of a cycle run on one stream each; with the default of 8 queues two of them can share one).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -389,6 +393,7 @@ def main():
             "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args.workload, inp, world, P),
             "ms_per_round": round_ms / max(1, n_launch),
             "cycle": {"pools_in_flight_per_gpu": len(mine), "ms_per_cycle_device": tm[0] / args.steps, "ms_per_cycle_wall": wall_ms / args.steps,
+                      "round_ms_by_pool_last_step": [round(st.device_ms, 2) for st in stats_list],
                       "note": "a round is one persistent CTA on one SM; the pools of a cycle a rank owns run concurrently (up to 8 per GPU). "
                               "ms_per_round is the latency of ONE round (CUDA events on its stream) while the others run"},
             "placements_per_round": int(placements / max(1, n_launch)),
