@@ -155,6 +155,11 @@ struct DevPtrs {
   uint2* bt_seq;                   // merged sequence: {job, class}
   uint32_t* bt_node;               // (unused)
   int64_t* bt_asum;                // [2][Q][MAX_RESOURCES] requests of every queue's items below the horizon, per batch buffer
+  uint32_t* bt_card;               // [2][Q * bt_wq] members of the item (1 = single job, > 1 = a simple gang)
+  uint4* bt_item;                  // [2][Q * bt_wq] merged order: {queue, stream position of the item's last job, members, 0}
+  uint32_t* bt_gnode;              // [2][Q * bt_wq][64] merged order: the nodes of a gang item's members
+  uint32_t* gang_bak;              // the window a gang's candidates come from, as it was when the gang started (32 entries)
+  const uint8_t* gang_simple;      // [G] every member queued, complete, one class, contiguous in its queue (batchable)
   uint32_t* undo_log;              // [5 * J] txn undo records
   // fair preemption scratch
   int64_t* fp_avail;               // [D][N]

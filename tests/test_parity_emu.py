@@ -175,6 +175,30 @@ def test_long_batch_pipelines(wq, seed, lane_order, compare_key):
         os.environ.pop("ARMADA_BT_WQ", None)
 
 
+@pytest.mark.parametrize("nodes,queues,jobs,wq,seed", [(60, 4, 1500, 0, 1), (120, 8, 3000, 8, 2), (250, 6, 5000, 16, 3), (40, 3, 900, 0, 4)])
+def test_gangs_as_batch_items(nodes, queues, jobs, wq, seed, lane_order, compare_key):
+    """Simple gangs (complete, one class, contiguous in their queue — what the C4 generator makes) are
+    ordered by the batch pipeline as ONE item and placed member by member by the assignment loop, all or
+    nothing: the clusters here fill up, so gangs fail in the middle (roll-back of the table, of the
+    touched bits and of the window a refill replaced) and the general loop fails them the reference's way."""
+    if wq:
+        os.environ["ARMADA_BT_WQ"] = str(wq)
+    try:
+        dev = emu_lib.emu_round()
+        r = synth.config_c4(nodes, queues, jobs, seed=synth.SEED + seed)
+        inp = r.to_input()
+        want = oracle_lib.round_schedule(inp)
+        got = dev.schedule(inp)
+        bad = got.diff(want)
+        assert not bad, f"C4 {nodes}x{jobs}: emulated kernel != oracle:\n  " + "\n  ".join(bad)
+        # gang members were placed in batch mode: more placements than iterations there
+        assert int(got.stats.placements) > int(got.stats.loop_iterations) - int(np.count_nonzero(np.asarray(want.job_state) == 4))
+        assert int(got.stats.phase_cycles[4]) > 0
+        dev.close()
+    finally:
+        os.environ.pop("ARMADA_BT_WQ", None)
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_exact_mode_unaligned_rounds(seed, lane_order):
     """Inputs outside the fast domain run in exact mode: the reference's default index resolutions
