@@ -167,8 +167,8 @@ struct DevPtrs {
   uint32_t* fp_head;               // [N] most recent visited evicted index on the node
   uint32_t* fp_next;               // [J] chain by evicted index
   uint32_t* nver;                  // [N] changes of the node's rows / evicted jobs so far (trigger caches)
-  uint32_t* fc_ver;                // [8][N] nver the cached trigger was computed at
-  int32_t* fc_trig;                // [8][N] cached fair-preemption trigger index (-1 none)
+  uint32_t* fc_ver;                // [8][N] pairs {nver the cached trigger was computed at, cached fair-preemption trigger index (-1 none)}
+  int32_t* fc_trig;                // (unused)
   uint8_t* fp_bad;                 // [N] static requirements not met (valid when epoch matches)
   // ---- queue / sctx state persisted between kernels ----
   int64_t* q_alloc;                // [Q][D]

@@ -35,4 +35,6 @@ with DeviceRound(0) as dev:
                           "chain_busy_wait_per_iter": [round(int(best.batch_debug[i]) / it, 1) for i in range(2)], "runs_cut": [int(best.batch_debug[2]), int(best.batch_debug[3])],
                           "slow_steps": int(best.batch_debug[4]), "cycles_per_slow_step": round(int(best.batch_debug[5]) / max(1, int(best.batch_debug[4]))),
                           "refills": int(best.batch_debug[6]), "cycles_per_refill": round(int(best.batch_debug[7]) / max(1, int(best.batch_debug[6]))),
-                          "fair_scans": int(best.fair_preemption_scans), "ev1": int(best.evicted_pass1), "ev2": int(best.evicted_pass2)}), flush=True)
+                          "fair_scans": int(best.fair_preemption_scans), "ev1": int(best.evicted_pass1), "ev2": int(best.evicted_pass2),
+                          "probes": int(best.probes), "rescans": int(best.tree_rescans),
+                          "phase_mcycles": [round(int(best.phase_cycles[i]) / 1e6, 1) for i in range(8)]}), flush=True)
