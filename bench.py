@@ -37,6 +37,9 @@ import time
 # Before anything creates the CUDA context: one hardware work queue per concurrent round (the pools
 # of a cycle run on one stream each; with the default of 8 queues two of them can share one).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version to STDOUT, in front of the one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np
 
