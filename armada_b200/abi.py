@@ -199,6 +199,8 @@ def declare_prototypes(lib: C.CDLL) -> None:
     lib.armada_nodedb_create.restype = C.c_int32
     lib.armada_nodedb_schedule_many.argtypes = [vp, C.c_uint32, u32p, u32p, u8p, u32p]
     lib.armada_nodedb_schedule_many.restype = C.c_int32
+    lib.armada_nodedb_select_nodes.argtypes = [vp, C.c_uint32, u32p, u32p]
+    lib.armada_nodedb_select_nodes.restype = C.c_int32
     lib.armada_nodedb_destroy.argtypes = [vp]
     lib.armada_nodedb_destroy.restype = C.c_int32
     lib.armada_strerror.argtypes = [C.c_int32]
@@ -234,6 +236,7 @@ PRODUCT_SYMBOLS = [
     "armada_round_schedule",
     "armada_nodedb_create",
     "armada_nodedb_schedule_many",
+    "armada_nodedb_select_nodes",
     "armada_nodedb_destroy",
     "armada_strerror",
     "armada_last_error",

@@ -121,6 +121,17 @@ class DeviceNodeDb:
         out_nodes = [node[int(start[g]):int(start[g + 1])].copy() for g in range(len(gangs))]
         return ok[: len(gangs)].astype(bool), out_nodes
 
+    def select_nodes(self, classes):
+        """One independent job per entry (its job class): the node it would be bound to on the empty
+        cluster, abi.NONE if it fits nowhere (SelectNodeForJobWithTxn, nodedb.go:431-512)."""
+        import numpy as np
+        cls = np.asarray(list(classes) or [0], dtype=np.uint32)
+        node = np.full(len(cls), abi.NONE, np.uint32)
+        st = self.lib.armada_nodedb_select_nodes(self.h, len(list(classes)), cls.ctypes.data_as(abi.u32p), node.ctypes.data_as(abi.u32p))
+        if st != abi.OK:
+            raise abi.ArmadaError(st, f"{self.lib.armada_strerror(st).decode()}: {self.lib.armada_last_error().decode()}")
+        return node[: len(list(classes))]
+
     def close(self):
         if self.h:
             self.lib.armada_nodedb_destroy(self.h)

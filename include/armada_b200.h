@@ -315,6 +315,10 @@ int32_t armada_nodedb_create(int32_t device, const ArmadaRoundInput* in, ArmadaN
  * placed on (caller's node numbering), ARMADA_NONE for the members of the others. */
 int32_t armada_nodedb_schedule_many(ArmadaNodeDb* db, uint32_t num_gangs, const uint32_t* gang_start, const uint32_t* member_class,
                                     uint8_t* ok, uint32_t* member_node);
+/* NodeDb.SelectNodeForJobWithTxn (nodedb.go:431-512) for num_jobs independent jobs against the empty
+ * cluster — what SubmitChecker does for a single job (submitcheck.go:353-371): node[i] = the node job i
+ * (a job-class index of `in`) would be bound to, ARMADA_NONE = it fits nowhere. */
+int32_t armada_nodedb_select_nodes(ArmadaNodeDb* db, uint32_t num_jobs, const uint32_t* job_class, uint32_t* node);
 int32_t armada_nodedb_destroy(ArmadaNodeDb* db);
 
 const char* armada_strerror(int32_t status);

@@ -271,6 +271,12 @@ def _dry_run_case(r, gangs_as_jobs, lib):
         want_nodes.append(nodes)
     with DeviceNodeDb(inp, 0, lib=lib) as db:
         got_ok, got_nodes = db.schedule_many([[int(jc[j]) for j in g] for g in gangs_as_jobs])
+        # armada_nodedb_select_nodes: the single-job form gives the same nodes as gangs of one
+        singles = [g for g in gangs_as_jobs if len(g) == 1]
+        sel = db.select_nodes([int(jc[g[0]]) for g in singles])
+        for g, n in zip(singles, sel):
+            ok, nodes = odb.dry_run(g)
+            assert (n != abi.NONE) == ok and (not ok or n == nodes[0])
     assert list(got_ok) == want_ok
     for g, (a, b) in enumerate(zip(got_nodes, want_nodes)):
         assert (a == b).all(), f"gang {g}: {a} vs {b}"

@@ -267,3 +267,70 @@ def test_dry_run_nodedb_resolution_rounding():
 def test_more_classes_than_the_shared_memory_table_holds():
     r = synth.many_classes_round(n_nodes=600, n_jobs=12000)
     assert_parity(r.to_input(), r.name)
+
+
+@pytest.mark.parametrize("seed", [2, 4, 10])
+def test_snapshot_construction_on_the_device(seed):
+    """NULL queue_allocated_by_pc / queue_constrained_demand: k_snapshot_jobs / k_snapshot_queues derive
+    the queue accounting from the job arrays (scheduling_algo.go:522-632,664-676)."""
+    limits = seed == 4
+    r = synth.random_round(seed, n_nodes=50, n_jobs=350, n_running=100, protected_fraction=0.5, queue_limits=limits)
+    inp = r.to_input()
+    explicit = oracle_lib.round_schedule(inp)
+    inp.queue_allocated_by_pc = None
+    inp.queue_constrained_demand = None
+    want = oracle_lib.round_schedule(inp)
+    got = cuda_round(inp)
+    assert not got.diff(want)
+    if not limits:
+        assert not want.diff(explicit)
+
+
+def test_snapshot_construction_at_c5_scale():
+    r = synth.scaled("C5", 0.05)
+    inp = r.to_input()
+    inp.queue_allocated_by_pc = None
+    inp.queue_constrained_demand = None
+    assert_parity(inp, "C5@0.05 with derived queue accounting")
+
+
+def test_time_budget_aborts_the_round_and_leaves_the_snapshot_runnable():
+    """armada_round_run_deadline on the device (%globaltimer): a budget that cannot be met returns
+    ARMADA_E_DEADLINE, download is refused, the same handle then schedules the snapshot bit-exactly."""
+    r = synth.scaled("C3", 0.05)
+    inp = r.to_input()
+    with DeviceRound(0) as dev:
+        dev.upload(inp)
+        with pytest.raises(abi.ArmadaError) as ei:
+            dev.run(budget_ns=1000)
+        assert ei.value.status == abi.E_DEADLINE
+        with pytest.raises(abi.ArmadaError) as ei:
+            dev.download()
+        assert ei.value.status == abi.E_STATE
+        dev.run(budget_ns=60_000_000_000)
+        assert not dev.download().diff(oracle_lib.round_schedule(inp))
+
+
+@pytest.mark.parametrize("nodes,queues,jobs,seed", [(60, 4, 1500, 1), (250, 6, 5000, 3), (3000, 16, 40000, 5)])
+def test_gangs_as_batch_items(nodes, queues, jobs, seed):
+    """Simple gangs are items of the batch pipeline (placed member by member, all or nothing); the
+    clusters fill up, so gangs also fail in the middle and are rolled back."""
+    r = synth.config_c4(nodes, queues, jobs, seed=synth.SEED + seed)
+    got, want = assert_parity(r.to_input(), f"C4 {nodes}x{jobs}")
+    assert int(got.stats.placements) > int(got.stats.loop_iterations) - int(np.count_nonzero(np.asarray(want.job_state) == 4))
+
+
+def test_rounds_of_different_handles_run_concurrently_and_stay_exact():
+    """Four pools on one GPU at the same time (one handle and one host thread each, pools.PoolCycle):
+    every result equals the oracle's, whatever the interleaving."""
+    from armada_b200.pools import PoolCycle
+    pools = [synth.random_round(900 + i, n_nodes=200 + 50 * i, n_queues=6, n_jobs=6000, n_running=0, gangs=i % 2 == 1, priorities=False).to_input()
+             for i in range(4)]
+    cyc = PoolCycle(pools, 0, 1, lambda: DeviceRound(0))
+    try:
+        for _ in range(3):
+            out = cyc.schedule_cycle()
+            for p, inp in enumerate(pools):
+                assert not out[p].diff(oracle_lib.round_schedule(inp)), f"pool {p}"
+    finally:
+        cyc.close()
