@@ -9,6 +9,8 @@ import os
 
 ABI_VERSION = 1
 MAX_RESOURCES = 8
+EXCLUDED_KINDS = 5  # ARMADA_EXCL_*: node type, static, resources (reached), implicit, disallowed
+EXCL_NODE_TYPE, EXCL_STATIC, EXCL_RESOURCES, EXCL_IMPLICIT, EXCL_DISALLOWED = range(5)
 MAX_PRIORITIES = 16
 MAX_PRIORITY_CLASSES = 32
 MAX_AWAY = 4
@@ -69,7 +71,7 @@ class RoundInput(C.Structure):
         ("disable_away_scheduling", C.c_uint8),
         ("disable_gang_away_scheduling", C.c_uint8),
         ("global_limiter_is_inf", C.c_uint8),
-        ("_pad0", C.c_uint8),
+        ("collect_excluded_nodes", C.c_uint8),
         ("max_resources_to_schedule", C.c_int64 * MAX_RESOURCES),
         ("protected_fraction_of_fair_share", C.c_double),
         ("max_queue_lookback", C.c_uint32),
@@ -139,6 +141,7 @@ class RoundOutput(C.Structure):
         ("queue_fair_share", f64p),
         ("scheduled_resources", i64p),
         ("evicted_resources", i64p),
+        ("job_excluded_nodes", u32p),
         ("num_scheduled_jobs", C.c_uint32),
         ("num_scheduled_gangs", C.c_uint32),
         ("num_evicted_jobs", C.c_int32),

@@ -44,6 +44,7 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
                                             // ordered walks over per-level rounded keys (Ctl::scan_probe_exact), no sorted index / batches
   int64_t index_res[ARMADA_MAX_RESOURCES];  // exact mode: index resolution of the i-th indexed resource (raw units)
   int32_t park_mates;                       // measurement knob (ARMADA_PARK_MATES): see Batch::produce
+  int32_t collect_excl;                     // keep NumExcludedNodesByReason of the jobs that fail (DevPtrs.excl)
   int32_t k32_ok;                           // … and the resource fields without guard bits fit 26 bits (32-bit compare keys)
   int32_t priorities[ARMADA_MAX_PRIORITIES];
   ArmadaPriorityClass pcs[ARMADA_MAX_PRIORITY_CLASSES];
@@ -160,6 +161,8 @@ struct DevPtrs {
   uint32_t* bt_gnode;              // [2][Q * bt_wq][64] merged order: the nodes of a gang item's members
   uint32_t* gang_bak;              // the window a gang's candidates come from, as it was when the gang started (32 entries)
   const uint8_t* gang_simple;      // [G] every member queued, complete, one class, contiguous in its queue (batchable)
+  uint32_t* excl;                  // [J][ARMADA_EXCLUDED_KINDS] NumExcludedNodesByReason by kind of the failed single jobs (collect_excl)
+  const uint32_t* row_type_excl;   // [rows] nodes of the node types the row does not match (NodeTypesMatchingJob)
   uint32_t* undo_log;              // [5 * J] txn undo records
   // fair preemption scratch
   int64_t* fp_avail;               // [D][N]

@@ -694,6 +694,7 @@ class RoundResult:
         self.queue_fair_share = np.zeros((Q, 3), np.float64)
         self.scheduled_resources = np.zeros(D, np.int64)
         self.evicted_resources = np.zeros(D, np.int64)
+        self.job_excluded_nodes = np.zeros((J, abi.EXCLUDED_KINDS), np.uint32)
         o = abi.RoundOutput()
         o.job_state = self.job_state.ctypes.data_as(abi.u8p)
         o.job_node = self.job_node.ctypes.data_as(abi.u32p)
@@ -708,13 +709,15 @@ class RoundResult:
         o.queue_fair_share = self.queue_fair_share.ctypes.data_as(abi.f64p)
         o.scheduled_resources = self.scheduled_resources.ctypes.data_as(abi.i64p)
         o.evicted_resources = self.evicted_resources.ctypes.data_as(abi.i64p)
+        if inp.collect_excluded_nodes:
+            o.job_excluded_nodes = self.job_excluded_nodes.ctypes.data_as(abi.u32p)
         self.out = o
         self.stats = abi.RoundStats()
         self.num_jobs = inp.num_jobs
 
     ARRAYS = ("job_state", "job_node", "job_scheduled_at_priority", "job_preempted_at_priority", "job_method",
               "job_reason", "job_seq", "node_alloc", "queue_allocated", "queue_allocated_by_pc", "queue_fair_share",
-              "scheduled_resources", "evicted_resources")
+              "scheduled_resources", "evicted_resources", "job_excluded_nodes")
     SCALARS = ("num_scheduled_jobs", "num_scheduled_gangs", "num_evicted_jobs", "termination_reason",
                "num_result_scheduled", "num_result_preempted")
 

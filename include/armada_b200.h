@@ -100,6 +100,10 @@ enum {
   ARMADA_REASON_NO_REMAINING_CANDIDATES = 12     /* termination only */
 };
 
+/* kinds of ArmadaRoundOutput.job_excluded_nodes */
+#define ARMADA_EXCLUDED_KINDS 5u
+enum { ARMADA_EXCL_NODE_TYPE = 0, ARMADA_EXCL_STATIC = 1, ARMADA_EXCL_RESOURCES = 2, ARMADA_EXCL_IMPLICIT = 3, ARMADA_EXCL_DISALLOWED = 4 };
+
 /* node flags */
 #define ARMADA_NODE_UNSCHEDULABLE 1u /* Node.unschedulable (carries the unschedulable taint) */
 #define ARMADA_NODE_OVERALLOCATED 2u /* Node.overAllocated, scheduling_algo.go:911-916        */
@@ -143,7 +147,8 @@ typedef struct {
   uint8_t disable_away_scheduling;
   uint8_t disable_gang_away_scheduling;
   uint8_t global_limiter_is_inf;                       /* rate.Limit == Inf ⇒ ReserveN is a no-op */
-  uint8_t _pad0;
+  uint8_t collect_excluded_nodes;                      /* 1 ⇒ keep PodSchedulingContext.NumExcludedNodesByReason of the
+                                                          jobs that fail (ArmadaRoundOutput.job_excluded_nodes)   */
   int64_t max_resources_to_schedule[ARMADA_MAX_RESOURCES]; /* constraints.go:213-229 */
   double protected_fraction_of_fair_share;
   uint32_t max_queue_lookback;                         /* 0 = unlimited */
@@ -235,6 +240,17 @@ typedef struct {
   double* queue_fair_share;      /* [Q][3] FairShare, DemandCappedAdjusted, UncappedAdjusted  */
   int64_t* scheduled_resources;  /* [D] sctx.ScheduledResources                               */
   int64_t* evicted_resources;    /* [D] sctx.EvictedResources                                 */
+  /* PodSchedulingContext.NumExcludedNodesByReason (context/pod.go:51, filled at nodedb.go:445-480, 605-640,
+   * 786-797, 1102-1117) of the single (non-gang) jobs whose scheduling attempt FAILED, as a histogram over
+   * reason KINDS — the reference's map keys are strings that embed taints, labels and quantities; the
+   * kinds are their classes: [ARMADA_EXCL_NODE_TYPE] nodes of node types the job does not match
+   * (NodeTypesMatchingJob), [ARMADA_EXCL_STATIC] nodes the ordered walk reached at the last priority
+   * tried and StaticJobRequirementsMet rejected for a taint / label / affinity, [ARMADA_EXCL_RESOURCES]
+   * nodes it reached and rejected for resources, [ARMADA_EXCL_IMPLICIT] the nodes it never reached
+   * ("insufficient resources" added by the deferred function, nodedb.go:449-462), [ARMADA_EXCL_DISALLOWED]
+   * disallowedResourceRequested.  The kinds of an attempted job sum to num_nodes
+   * (queue_scheduler_test.go:656-676); all zero for every other job.  Needs collect_excluded_nodes.  */
+  uint32_t* job_excluded_nodes;  /* [J][ARMADA_EXCLUDED_KINDS], or NULL                          */
   uint32_t num_scheduled_jobs;   /* sctx.NumScheduledJobs                                     */
   uint32_t num_scheduled_gangs;  /* sctx.NumScheduledGangs                                    */
   int32_t num_evicted_jobs;      /* sctx.NumEvictedJobs                                       */

@@ -72,6 +72,8 @@ struct JobCtx {
   int32_t p_preempted_at = MIN_PRIORITY;
   uint8_t p_method = ARMADA_METHOD_NONE;
   bool p_away = false;
+  // PodSchedulingContext.NumExcludedNodesByReason (context/pod.go:51) by reason KIND (ARMADA_EXCL_*)
+  uint32_t excl[ARMADA_EXCLUDED_KINDS] = {0, 0, 0, 0, 0};
   bool is_successful() const { return reason == ARMADA_REASON_NONE; }  // job.go:113-115
   bool pctx_successful() const { return has_pctx && p_node != NONE; }  // pod.go:59-61
 };
@@ -94,6 +96,7 @@ struct NodeDb {
   std::vector<int64_t> alloc;            // [PL][D][N]  Node.AllocatableByPriority
   std::vector<int64_t> cur_key;          // [N][PL][R]  Node.Keys
   std::vector<IndexSet> index;           // [PL][T]     memdb index per priority (+type prefix)
+  std::vector<uint32_t> nodes_of_type;   // [T]         numNodesByNodeType (nodedb.go:1148-1159)
   std::vector<std::vector<uint32_t>> node_jobs;  // keys of Node.AllocatedByJobId
   std::vector<uint32_t> bound_node;      // [J] node whose AllocatedByJobId holds the job
   std::vector<uint8_t> evicted_on_node;  // [J] Node.EvictedJobRunIds
@@ -163,6 +166,8 @@ struct NodeDb {
     cur_key.assign((size_t)N * PL * R, 0);
     index.assign((size_t)PL * T, IndexSet(KeyLess{R}));
     node_jobs.resize(N);
+    nodes_of_type.assign((size_t)T, 0);
+    for (uint32_t n = 0; n < N; ++n) nodes_of_type[in->node_type[n]]++;
     bound_node.assign(J, NONE);
     evicted_on_node.assign(J, 0);
     sched_prio.assign(J, 0);
@@ -501,6 +506,11 @@ struct NodeDb {
     int p = level_of(priority);
     TypesIt m;
     types_it_init(m, jc.row, p, ireq);
+    // pctx.NumExcludedNodesByReason = Clone(what NodeTypesMatchingJob excluded) (nodedb.go:605-640) + one
+    // per node the walk reaches and JobRequirementsMet rejects (:786-797)
+    for (uint32_t k = 0; k < ARMADA_EXCLUDED_KINDS; ++k) jc.excl[k] = 0;
+    for (uint32_t t = 0; t < (uint32_t)T; ++t)
+      if (!type_matches(jc.row, t)) jc.excl[ARMADA_EXCL_NODE_TYPE] += nodes_of_type[t];  // :1102-1117
     for (uint32_t n = types_it_next(m); n != NONE; n = types_it_next(m)) {
       // JobRequirementsMet, nodematching.go:147-157
       if (static_met(n, jc.row, rq) && dynamic_met_at(n, p, rq)) {
@@ -508,7 +518,18 @@ struct NodeDb {
         jc.p_preempted_at = priority;
         return n;
       }
+      // StaticJobRequirementsMet checks taints, labels and affinity before the total resources (:161-190)
+      const bool string_predicates = row_bit(in->static_match, jc.row, (in->num_static_classes + 31) / 32, in->node_static_class[n]);
+      jc.excl[string_predicates ? ARMADA_EXCL_RESOURCES : ARMADA_EXCL_STATIC] += 1;
     }
+    return NONE;
+  }
+  // the deferred function of SelectNodeForJobWithTxn (nodedb.go:449-462): a pod that found no node counts
+  // the nodes nothing excluded explicitly as "insufficient resources"
+  uint32_t fail_select(JobCtx& jc) {
+    uint32_t expl = 0;
+    for (uint32_t k = 0; k < ARMADA_EXCLUDED_KINDS; ++k) expl += jc.excl[k];
+    if (N > expl) jc.excl[ARMADA_EXCL_IMPLICIT] += N - expl;
     return NONE;
   }
 
@@ -698,6 +719,7 @@ struct NodeDb {
     jc.p_preempted_at = MIN_PRIORITY;
     jc.p_method = ARMADA_METHOD_NONE;
     jc.p_away = false;
+    for (uint32_t k = 0; k < ARMADA_EXCLUDED_KINDS; ++k) jc.excl[k] = 0;
     const int64_t* rq = req_of(jc.job);
     if (jc.assigned_node != NONE) {  // :465-476 + selectNodeForPodWithItAtPriority(onlyDynamic)
       uint32_t n = jc.assigned_node;
@@ -714,10 +736,14 @@ struct NodeDb {
         jc.p_preempted_at = priority;
         return n;
       }
-      return NONE;
+      jc.excl[ARMADA_EXCL_RESOURCES] = 1;  // selectNodeForPodWithItAtPriority on the one node (:786-797)
+      return fail_select(jc);
     }
     for (int d = 0; d < D; ++d)  // :478-483
-      if (((in->disallowed_resource_mask >> d) & 1u) && rq[d] > 0) return NONE;
+      if (((in->disallowed_resource_mask >> d) & 1u) && rq[d] > 0) {
+        jc.excl[ARMADA_EXCL_DISALLOWED] = N;
+        return fail_select(jc);
+      }
     if (!in->disable_home_scheduling) {
       uint32_t n = select_home_or_away_at_priority(jc);
       if (n != NONE) return n;
@@ -745,7 +771,7 @@ struct NodeDb {
         jc.has_additional = saved_additional;
       }
     }
-    return NONE;
+    return fail_select(jc);
   }
 
   // ScheduleManyWithTxn, nodedb.go:386-418
@@ -1679,6 +1705,10 @@ struct Round {
       if (out->job_method) out->job_method[j] = has ? jc.p_method : (uint8_t)ARMADA_METHOD_NONE;
       if (out->job_reason) out->job_reason[j] = unsuccessful[j] ? unsuccessful_reason[j] : (uint8_t)ARMADA_REASON_NONE;
       if (out->job_seq) out->job_seq[j] = job_seq[j];
+      if (out->job_excluded_nodes && in->collect_excluded_nodes) {
+        const bool single_failed = st == ARMADA_JOB_FAILED && jc.job != NONE && jc.has_pctx && in->job_gang[j] == NONE;
+        for (uint32_t k = 0; k < ARMADA_EXCLUDED_KINDS; ++k) out->job_excluded_nodes[(size_t)j * ARMADA_EXCLUDED_KINDS + k] = single_failed ? jc.excl[k] : 0u;
+      }
     }
     if (out->node_alloc) std::memcpy(out->node_alloc, db.alloc.data(), db.alloc.size() * sizeof(int64_t));
     for (uint32_t q = 0; q < Q; ++q) {

@@ -333,3 +333,84 @@ def test_snapshot_construction_on_the_device(seed):
     assert not got.diff(want)
     if not limits:
         assert not want.diff(explicit)
+
+
+def _excluded_nodes_properties(inp, want):
+    """queue_scheduler_test.go:656-676: for a single job that could not be scheduled the excluded nodes
+    add up to the number of nodes; jobs that were never attempted (or did not fail) report nothing."""
+    ex = np.asarray(want.job_excluded_nodes)
+    st = np.asarray(want.job_state)
+    gang = np.ctypeslib.as_array(inp.job_gang, (inp.num_jobs,))
+    tot = ex.sum(axis=1)
+    assert (tot[(st != abi.JOB_FAILED) | (gang != abi.NONE)] == 0).all()
+    attempted = tot > 0
+    assert (tot[attempted] == inp.num_nodes).all()
+    return int(attempted.sum())
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_excluded_nodes_by_reason_kind(seed, lane_order):
+    """collect_excluded_nodes: PodSchedulingContext.NumExcludedNodesByReason of the jobs that fail, by
+    reason kind (node type / taints+labels / resources on a reached node / never reached), identical to
+    the oracle's restatement of nodedb.go:445-480,605-640,786-797,1102-1117."""
+    r = synth.random_round(700 + seed, n_nodes=40 + 7 * seed, n_queues=4, n_jobs=600, n_running=100 if seed % 2 else 0, gangs=seed % 3 == 0,
+                           priorities=seed % 2 == 1, unaligned=seed >= 6)
+    inp = r.to_input()
+    inp.collect_excluded_nodes = 1
+    want = oracle_lib.round_schedule(inp)
+    got = emu_round(inp)
+    assert not got.diff(want)
+    assert _excluded_nodes_properties(inp, want) > 0 or seed in (0,)
+
+
+def test_excluded_nodes_on_the_reference_tables():
+    """The same on the reference's QueueScheduler table (the test that states the property)."""
+    seen = []
+
+    def schedule(inp):
+        inp.collect_excluded_nodes = 1
+        got = _emu_round_or_skip(inp)  # (compares every array, job_excluded_nodes included, with the oracle)
+        seen.append(_excluded_nodes_properties(inp, got))
+        return got
+
+    for name in sorted(QS.keys()):
+        try:
+            gt.run_queue_scheduler_case(QS[name], schedule)
+        except gt.UnsupportedCase:
+            continue
+    assert sum(seen) > 0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_excluded_nodes_static_and_resource_kinds(seed, lane_order):
+    """Static classes finer than node types (a taint / label the node type index does not carry): nodes of a
+    matching node type that the walk reaches and StaticJobRequirementsMet rejects count under
+    ARMADA_EXCL_STATIC; with a resource that is not indexed, reached nodes can also fail on resources."""
+    r = synth.random_round(740 + seed, n_nodes=60, n_queues=3, n_jobs=500, n_running=0, gangs=False, priorities=False)
+    if seed == 2:
+        r.indexed = [synth.CPU, synth.MEM]  # gpu is not in the index: a reached node can still lack gpus
+    # half of the nodes of type 0 get a new static class that row 0 rejects (type_match still accepts their type)
+    sc = np.asarray(r.node_static_class).astype(np.uint32).copy()
+    typ = np.asarray(r.node_type).astype(np.uint32)
+    new = r.num_static_classes
+    pick = np.nonzero(typ == 0)[0][::2]
+    sc[pick] = new
+    sm = np.asarray(r.static_match).astype(np.uint32)
+    rows = sm.shape[0]
+    words = (new + 1 + 31) // 32
+    sm2 = np.zeros((rows, words), np.uint32)
+    for row in range(rows):
+        for c in range(new):
+            if (sm[row, c >> 5] >> (c & 31)) & 1:
+                sm2[row, c >> 5] |= np.uint32(1 << (c & 31))
+        if row != 0 and (sm[row, 0] & 1):  # the new class behaves like class 0, except for row 0
+            sm2[row, new >> 5] |= np.uint32(1 << (new & 31))
+    r.node_static_class, r.static_match, r.num_static_classes = sc, sm2, new + 1
+    inp = r.to_input()
+    inp.collect_excluded_nodes = 1
+    want = oracle_lib.round_schedule(inp)
+    got = emu_round(inp)
+    assert not got.diff(want)
+    assert _excluded_nodes_properties(inp, want) > 0
+    ex = np.asarray(want.job_excluded_nodes)
+    assert ex[:, abi.EXCL_STATIC].sum() > 0

@@ -334,3 +334,28 @@ def test_rounds_of_different_handles_run_concurrently_and_stay_exact():
                 assert not out[p].diff(oracle_lib.round_schedule(inp)), f"pool {p}"
     finally:
         cyc.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_excluded_nodes_by_reason_kind(seed):
+    """collect_excluded_nodes: NumExcludedNodesByReason of the failed single jobs by reason kind, equal to
+    the oracle's; the kinds of an attempted job add up to the number of nodes
+    (queue_scheduler_test.go:656-676)."""
+    r = synth.random_round(700 + seed, n_nodes=40 + 7 * seed, n_queues=4, n_jobs=600, n_running=100 if seed % 2 else 0, gangs=seed % 3 == 0,
+                           priorities=seed % 2 == 1, unaligned=seed >= 4)
+    inp = r.to_input()
+    inp.collect_excluded_nodes = 1
+    got, want = assert_parity(inp, r.name)
+    ex = np.asarray(got.job_excluded_nodes)
+    tot = ex.sum(axis=1)
+    assert (tot[np.asarray(got.job_state) != abi.JOB_FAILED] == 0).all()
+    assert (tot[tot > 0] == inp.num_nodes).all() and (tot > 0).any()
+
+
+def test_excluded_nodes_at_c3_scale():
+    r = synth.scaled("C3", 0.05)
+    inp = r.to_input()
+    inp.collect_excluded_nodes = 1
+    got, _ = assert_parity(inp, "C3@0.05 with excluded-node kinds")
+    tot = np.asarray(got.job_excluded_nodes).sum(axis=1)
+    assert (tot[tot > 0] == inp.num_nodes).all() and (tot > 0).any()
