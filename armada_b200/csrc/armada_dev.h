@@ -171,7 +171,9 @@ struct DevPtrs {
   uint32_t* fp_next;               // [J] chain by evicted index
   uint32_t* nver;                  // [N] changes of the node's rows / evicted jobs so far (trigger caches)
   uint32_t* fc_ver;                // [8][N] pairs {nver the cached trigger was computed at, cached fair-preemption trigger index (-1 none)}
-  int32_t* fc_trig;                // (unused)
+  uint32_t* bver;                  // [ceil(N/256)] changes of any node of the 256-node block (sum of its nver)
+  uint32_t* fc_bver;               // [8][ceil(N/256)] bver the block's cached maximum was computed at
+  unsigned long long* fc_bmax;     // [8][ceil(N/256)] largest (trigger + 1) << 32 | node of the block, 0 = none
   uint8_t* fp_bad;                 // [N] static requirements not met (valid when epoch matches)
   // ---- queue / sctx state persisted between kernels ----
   int64_t* q_alloc;                // [Q][D]
