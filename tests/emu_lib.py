@@ -5,6 +5,7 @@ under armada_b200/ loads this library."""
 from __future__ import annotations
 
 import ctypes as C
+import fcntl
 import os
 import subprocess
 
@@ -21,12 +22,21 @@ _lib = None
 def build(force: bool = False) -> None:
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".inc", ".h"))]
     srcs += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "armada_b200.h")]
-    stale = not os.path.exists(EMU_LIB) or any(os.path.getmtime(p) > os.path.getmtime(EMU_LIB) for p in srcs)
-    if force or stale:
-        subprocess.run(
-            ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DARMADA_EMU", "-x", "c++",
-             os.path.join(CSRC, "armada_round.cu"), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", EMU_DIR,
-             "-o", EMU_LIB, "-lpthread"], check=True)
+    def stale() -> bool:
+        return not os.path.exists(EMU_LIB) or any(os.path.getmtime(p) > os.path.getmtime(EMU_LIB) for p in srcs)
+
+    if not (force or stale()):
+        return
+    # pytest-xdist workers race for the build: one builds (to a temporary name, renamed into place), the others wait
+    with open(EMU_LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or stale():
+            tmp = f"{EMU_LIB}.{os.getpid()}.tmp"
+            subprocess.run(
+                ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DARMADA_EMU", "-x", "c++",
+                 os.path.join(CSRC, "armada_round.cu"), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", EMU_DIR,
+                 "-o", tmp, "-lpthread"], check=True)
+            os.replace(tmp, EMU_LIB)
 
 
 def load() -> C.CDLL:
