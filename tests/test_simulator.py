@@ -1,0 +1,164 @@
+"""armada_b200.simulator: the reference's simulator scenarios
+(internal/scheduler/simulator/simulator_test.go:34-520) replayed through the event loop, YAML specs of
+the reference's schema, parquet sinks.  CPU tests drive the loop with the oracle as the round engine
+(host logic only); the GPU tests run the product engine and compare it with the oracle-driven run."""
+import os
+
+import pytest
+
+import fixtures as fx
+import oracle_lib
+from armada_b200 import simulator as sim
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIMDIR = os.path.join(HERE, "golden", "sim")
+MIN = 60 * sim.NS
+
+
+def oracle_engine(inp):
+    return oracle_lib.round_schedule(inp)
+
+
+def node32(n):  # NodeTemplate32Cpu, test_utils.go:94-104
+    return sim.NodeTemplate(n, {"cpu": "32", "memory": "256Gi"})
+
+
+def jt32(n, job_set, pc, **kw):  # JobTemplate32Cpu, test_utils.go:141-157
+    return dict(number=n, job_set=job_set, priority_class_name=pc, requests={"cpu": "32", "memory": "256Gi"},
+                runtime=sim.ShiftedExponential(minimum=MIN), **kw)
+
+
+def workload(*queues):
+    qs = []
+    for name, templates in queues:
+        ts = [sim.JobTemplate(id=t.pop("id", f"{name}-{i}"), queue=name, **t) for i, t in enumerate(templates)]
+        qs.append(sim.Queue(name, 1.0, ts))
+    return sim.WorkloadSpec("w", qs, random_seed=1)
+
+
+def cluster(*clusters):
+    return sim.ClusterSpec("basic", [sim.Cluster(name, "TestPool", [node32(n)]) for name, n in clusters])
+
+
+def summary(s):
+    """EventSequencesSummary (test_utils.go:228-262) collapsed to (kind, queue) runs."""
+    out = []
+    for t in s.transitions:
+        if out and out[-1][0] == t.kind and out[-1][1] == t.queue:
+            out[-1][2] += 1
+        else:
+            out.append([t.kind, t.queue, 1])
+    return [tuple(x) for x in out]
+
+
+DEFAULT = fx.PriorityClass3  # testfixtures.TestDefaultPriorityClass
+SCENARIOS = {
+    # simulator_test.go:34-60
+    "Two jobs in parallel": (cluster(("TestCluster", 2)), lambda: workload(("A", [jt32(2, "foo", DEFAULT)])), 5,
+                             [("submit", "A", 2), ("leased", "A", 2), ("succeeded", "A", 2)]),
+    # :61-88
+    "Two jobs in sequence": (cluster(("TestCluster", 1)), lambda: workload(("A", [jt32(2, "foo", DEFAULT)])), 5,
+                             [("submit", "A", 2), ("leased", "A", 1), ("succeeded", "A", 1), ("leased", "A", 1), ("succeeded", "A", 1)]),
+    # :89-112
+    "10 jobs in sequence": (cluster(("TestCluster", 1)), lambda: workload(("A", [jt32(10, "foo", DEFAULT)])), 20,
+                            [("submit", "A", 10)] + [("leased", "A", 1), ("succeeded", "A", 1)] * 10),
+    # :113-150 (two clusters, one pool)
+    "Multiple Clusters": (cluster(("ClusterA", 1), ("ClusterB", 1)), lambda: workload(("A", [jt32(2, "foo", DEFAULT)])), 5,
+                          [("submit", "A", 2), ("leased", "A", 2), ("succeeded", "A", 2)]),
+    # :152-190
+    "JobTemplate dependencies": (cluster(("TestCluster", 3)),
+                                 lambda: workload(("A", [jt32(2, "foo", DEFAULT, id="jobTemplate"), jt32(1, "foo", DEFAULT, dependencies=["jobTemplate"])])), 5,
+                                 [("submit", "A", 2), ("leased", "A", 2), ("succeeded", "A", 2), ("submit", "A", 1), ("leased", "A", 1), ("succeeded", "A", 1)]),
+    # :191-232
+    "Preemption": (cluster(("TestCluster", 2)),
+                   lambda: workload(("A", [jt32(2, "foo", fx.PriorityClass0)]), ("B", [jt32(1, "bar", fx.PriorityClass0, earliest_submit_time=30 * sim.NS)])), 5,
+                   [("submit", "A", 2), ("leased", "A", 2), ("submit", "B", 1), ("preempted", "A", 1), ("leased", "B", 1), ("submit", "A", 1),
+                    ("succeeded", "A", 1), ("leased", "A", 1), ("succeeded", "B", 1), ("succeeded", "A", 1)]),
+    # :480-520
+    "Preempted Gang Job": (cluster(("Cluster1", 8)),
+                           lambda: workload(("A", [jt32(8, "foo", fx.PriorityClass2, gang_cardinality=8)]),
+                                            ("B", [jt32(1, "bar", fx.PriorityClass3, earliest_submit_time=30 * sim.NS)])), 5,
+                           [("submit", "A", 8), ("leased", "A", 8), ("submit", "B", 1), ("preempted", "A", 8), ("leased", "B", 1), ("submit", "A", 8),
+                            ("succeeded", "B", 1), ("leased", "A", 8), ("succeeded", "A", 8)]),
+}
+
+
+def run_scenario(name, engine):
+    cl, wl, minutes, want = SCENARIOS[name]
+    s = sim.Simulator(cl, wl(), fx.test_scheduling_config(), engine=engine, hard_termination_minutes=minutes).run()
+    return s, want
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_reference_scenarios(name):
+    s, want = run_scenario(name, oracle_engine)
+    assert summary(s) == want
+
+
+def test_gangs_over_several_clusters_are_refused():
+    """"Gang Job" (simulator_test.go:441-479) needs the node-uniformity search over cluster names."""
+    with pytest.raises(sim.UnsupportedSpec):
+        sim.Simulator(cluster(("Cluster1", 8), ("Cluster2", 1)), workload(("A", [jt32(16, "foo", DEFAULT, gang_cardinality=8)])),
+                      fx.test_scheduling_config(), engine=oracle_engine)
+
+
+def test_yaml_specs_and_c1(tmp_path):
+    """BASELINE config C1 from YAML files of the reference's schema: 100 nodes x 32 cpu, one queue, 1000 jobs
+    of (1 cpu, 10Gi), a 2.5 % per-round limit, 5 minute jobs."""
+    out = str(tmp_path / "out")
+    s = sim.simulate_files(os.path.join(SIMDIR, "cluster_100x32.yaml"), os.path.join(SIMDIR, "workload_1k.yaml"),
+                           os.path.join(SIMDIR, "config_basic.yaml"), output_dir=out, engine=oracle_engine)
+    rows = s.sink.job_rows
+    assert len(rows) == 1000 and all(r.state == "SUCCEEDED" for r in rows)
+    assert all(r.finished_time - r.scheduled_time == 300 for r in rows)
+    assert all(r.cpu == 1.0 and r.memory == 10 * 2**30 and r.priority_class == "armada-default" for r in rows)
+    # maximumResourceFractionToSchedule 0.025 of 3200 cpu = 80 cpu; CheckRoundConstraints trips once the scheduled resources
+    # EXCEED the limit (constraints.go:113-130), i.e. after the 81st job of a cycle; 10 s cycles
+    per_cycle = {}
+    for r in rows:
+        per_cycle[r.scheduled_time] = per_cycle.get(r.scheduled_time, 0) + 1
+    assert sorted(per_cycle) == [10 * i for i in range(13)]
+    assert [per_cycle[10 * i] for i in range(13)] == [81] * 12 + [28]
+    import pyarrow.parquet as pq
+    jobs = pq.read_table(os.path.join(out, "jobs.parquet"))
+    assert jobs.num_rows == 1000
+    assert jobs.column_names == ["queue", "job_set", "job_id", "run_id", "priority_class", "cpu", "memory", "gpu", "ephemeral_storage",
+                                 "exit_code", "state", "submitted_time", "scheduled_time", "finished_time"]
+    qs = pq.read_table(os.path.join(out, "queue_stats.parquet"))
+    assert qs.column_names[:4] == ["ts", "queue", "pool", "fair_share"]
+    first = qs.slice(0, 1).to_pylist()[0]
+    assert first["queue"] == "A" and first["pool"] == "default" and first["num_scheduled"] == 81 and first["allocated_cpu"] == 81
+    assert first["fair_share"] == 1.0
+
+
+def test_duration_and_spec_parsing():
+    assert sim.parse_duration("5m") == 300 * sim.NS and sim.parse_duration("1h30m") == 5400 * sim.NS
+    assert sim.parse_duration("500ms") == sim.NS // 2 and sim.parse_duration(None) == 0
+    w = sim.workload_spec_from_dict({"queues": [{"name": "A", "weight": 2, "jobTemplates": [
+        {"number": 4, "gangCardinality": 2, "repeat": {"numTimes": 3, "period": "1m"}, "requirements": {"resourceRequirements": {"requests": {"cpu": 1}}}}]}]})
+    assert w.queues[0].job_templates[0].id == "A-0"
+    e = sim.expand_repeating_templates(w)
+    assert [t.id for t in e.queues[0].job_templates] == ["A-0-repeat-0", "A-0-repeat-1", "A-0-repeat-2"]
+    assert [t.earliest_submit_time for t in e.queues[0].job_templates] == [0, MIN, 2 * MIN]
+    with pytest.raises(ValueError):
+        sim.workload_spec_from_dict({"queues": [{"name": "A", "weight": 0, "jobTemplates": []}]})
+    with pytest.raises(ValueError):
+        sim.workload_spec_from_dict({"queues": [{"name": "A", "weight": 1, "jobTemplates": [{"number": 3, "gangCardinality": 2}]}]})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["Preemption", "Preempted Gang Job", "10 jobs in sequence"])
+def test_reference_scenarios_on_the_device(name):
+    s, want = run_scenario(name, sim.device_engine(0))
+    assert summary(s) == want
+
+
+@pytest.mark.gpu
+def test_c1_on_the_device_matches_the_oracle_driven_run():
+    args = (os.path.join(SIMDIR, "cluster_100x32.yaml"), os.path.join(SIMDIR, "workload_1k.yaml"), os.path.join(SIMDIR, "config_basic.yaml"))
+    dev = sim.simulate_files(*args, engine=sim.device_engine(0))
+    ref = sim.simulate_files(*args, engine=oracle_engine)
+    assert dev.rounds == ref.rounds and dev.rounds > 13
+    assert dev.sink.job_rows == ref.sink.job_rows
+    assert dev.sink.queue_rows == ref.sink.queue_rows
+    assert dev.transitions == ref.transitions
