@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_RESOURCES = 8
 EXCLUDED_KINDS = 5  # ARMADA_EXCL_*: node type, static, resources (reached), implicit, disallowed
 EXCL_NODE_TYPE, EXCL_STATIC, EXCL_RESOURCES, EXCL_IMPLICIT, EXCL_DISALLOWED = range(5)
@@ -27,7 +27,9 @@ METHOD_NONE, METHOD_RESCHEDULED, METHOD_NO_PREEMPTION, METHOD_FAIRSHARE, METHOD_
 (REASON_NONE, REASON_MAX_RESOURCES_SCHEDULED, REASON_MAX_RESOURCES_PER_QUEUE, REASON_GLOBAL_RATE_LIMIT,
  REASON_QUEUE_RATE_LIMIT, REASON_QUEUE_CORDONED, REASON_GLOBAL_RATE_LIMIT_GANG, REASON_QUEUE_RATE_LIMIT_GANG,
  REASON_GANG_EXCEEDS_GLOBAL_BURST, REASON_GANG_EXCEEDS_QUEUE_BURST, REASON_GANG_DOES_NOT_FIT,
- REASON_JOB_DOES_NOT_FIT, REASON_NO_REMAINING_CANDIDATES) = range(13)
+ REASON_JOB_DOES_NOT_FIT, REASON_NO_REMAINING_CANDIDATES, REASON_UNIFORMITY_LABEL_NOT_INDEXED,
+ REASON_NO_NODES_WITH_UNIFORMITY_LABEL, REASON_GANG_FITS_NO_UNIFORMITY_VALUE, REASON_FLOATING_RESOURCES) = range(17)
+LABEL_NOT_INDEXED = 0xFFFFFFFE
 
 NODE_UNSCHEDULABLE = 1
 NODE_OVERALLOCATED = 2
@@ -123,6 +125,16 @@ class RoundInput(C.Structure):
         ("queue_limiter_is_inf", u8p),
         ("queued_start", u32p),
         ("queued_order", u32p),
+        # ABI 2: gang node uniformity, floating resources
+        ("gang_uniformity_label", u32p),
+        ("num_uniformity_labels", C.c_uint32),
+        ("_pad_uniformity", C.c_uint32),
+        ("uniformity_value_start", u32p),
+        ("class_uniformity_row", u32p),
+        ("floating_resource_mask", C.c_uint32),
+        ("floating_limits_configured", C.c_uint8),
+        ("_pad_floating", C.c_uint8 * 3),
+        ("floating_limit", C.c_int64 * MAX_RESOURCES),
     ]
 
 

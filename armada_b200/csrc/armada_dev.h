@@ -64,6 +64,11 @@ struct DevCfg {  // small POD, lives in global memory, hot parts copied to smem
       off_ring, off_bt_k0, off_bt_k1, off_bt_id;
   int32_t bt_wq;  // batch mode: items per queue per batch (0 = batch mode off)
   int32_t bt_np;  // Q * bt_wq rounded up to a power of two (sort size)
+  // gang node uniformity / floating resources (gang_scheduler.go:143,154-223)
+  uint32_t uni_V;            // value slots over all uniformity labels (0 = no gang carries one)
+  uint32_t floating_mask;    // bit d: resource d is floating (never part of the node fit)
+  int32_t floating_configured;
+  int64_t floating_limit[ARMADA_MAX_RESOURCES];
 };
 
 struct DevPtrs {
@@ -160,6 +165,9 @@ struct DevPtrs {
   uint4* bt_item;                  // [2][Q * bt_wq] merged order: {queue, stream position of the item's last job, members, 0}
   uint32_t* bt_gnode;              // [2][Q * bt_wq][64] merged order: the nodes of a gang item's members
   uint32_t* gang_bak;              // the window a gang's candidates come from, as it was when the gang started (32 entries)
+  const uint32_t* gang_uni_label;  // [G] uniformity label of the gang (ARMADA_NONE, ARMADA_LABEL_NOT_INDEXED)
+  const uint32_t* uni_start;       // [L+1] value slots of label l
+  const uint32_t* class_uni_row;   // [C][uni_V][ARMADA_DEV_VARIANTS] static rows with the slot's node selector added
   const uint8_t* gang_simple;      // [G] every member queued, complete, one class, contiguous in its queue (batchable)
   uint32_t* excl;                  // [J][ARMADA_EXCLUDED_KINDS] NumExcludedNodesByReason by kind of the failed single jobs (collect_excl)
   const uint32_t* row_type_excl;   // [rows] nodes of the node types the row does not match (NodeTypesMatchingJob)

@@ -175,6 +175,13 @@ class PriorityClass:
     maximum_resource_fraction_per_queue: Dict[str, float] = field(default_factory=dict)
 
 
+@dataclass(frozen=True)
+class FloatingResource:
+    name: str
+    resolution: str = "1"
+    quantity: Optional[object] = None  # the pool's total; None = this pool is not listed for the resource
+
+
 @dataclass
 class SchedulingConfig:
     """The hot-path-relevant subset of configuration.SchedulingConfig (configuration.go:186-361)."""
@@ -199,9 +206,12 @@ class SchedulingConfig:
     disable_away_scheduling: bool = False
     disable_gang_away_scheduling: bool = False
     disallowed_resources: Sequence[str] = ()
+    # FloatingResources of THIS pool (configuration.FloatingResourceConfig): resources no node holds, limited per pool
+    floating_resources: Sequence["FloatingResource"] = ()
 
     def factory(self) -> ResourceListFactory:
-        return ResourceListFactory(self.supported_resource_types)
+        # NewResourceListFactory: the supported (Kubernetes) types, then the floating ones (resource_list_factory.go:41-53)
+        return ResourceListFactory(list(self.supported_resource_types) + [ResourceType(f.name, f.resolution) for f in self.floating_resources])
 
     def allowed_priorities(self) -> List[int]:
         """types.AllowedPriorities (common/types/scheduling.go:99-109): PC + away priorities, sorted, unique."""
@@ -238,6 +248,7 @@ class JobSpec:
     affinity: Optional[Tuple[Tuple[MatchExpression, ...], ...]] = None  # required node-affinity terms
     gang_id: Optional[str] = None
     gang_cardinality: int = 1
+    gang_node_uniformity_label: Optional[str] = None  # GangInfo.NodeUniformity() (jobdb/gang.go)
     node: Optional[str] = None  # id of the node the job runs on (None = queued)
     scheduled_at_priority: Optional[int] = None
     active_run_timestamp: int = 0
@@ -399,6 +410,7 @@ class RoundInputBuilder:
         class_pc: List[int] = []
         class_row: List[int] = []
         class_away: List[List[int]] = []
+        class_meta: List[Tuple[Tuple[Toleration, ...], Dict[str, str], object, List[Tuple[Toleration, ...]]]] = []
         job_class = np.zeros(len(self.jobs), dtype=np.uint32)
         for ji, j in enumerate(self.jobs):
             req = f.from_job(j.requests)
@@ -411,12 +423,43 @@ class RoundInputBuilder:
                 class_pc.append(self.pc_index[j.priority_class])
                 class_row.append(row_of(j.tolerations, j.node_selector, j.affinity))
                 aw = [abi.NONE] * abi.MAX_AWAY
+                extras: List[Tuple[Toleration, ...]] = []
                 for k in range(len(pc.away_node_types)):
                     extra = self._away_tolerations(pc, k, req)
+                    extras.append(extra)
                     if extra:
                         aw[k] = row_of(tuple(j.tolerations) + extra, j.node_selector, j.affinity)
                 class_away.append(aw)
+                class_meta.append((tuple(j.tolerations), dict(j.node_selector), j.affinity, extras))
             job_class[ji] = classes[key]
+        # ---- gang node uniformity (gang_scheduler.go:154-223): value slots per label, rows per (class, slot) ----
+        uni_labels: Dict[str, int] = {}
+        uni_values: List[List[str]] = []
+        uni_classes: Dict[int, set] = {}
+        for ji, j in enumerate(self.jobs):
+            lab = j.gang_node_uniformity_label
+            if not lab or j.gang_id is None or j.gang_cardinality <= 1 or lab not in indexed_labels:
+                continue
+            if lab not in uni_labels:  # nodeDb.IndexedNodeLabelValues(label) minus "" (:181-190)
+                uni_labels[lab] = len(uni_values)
+                uni_values.append(sorted({self._node_labels(n)[lab] for n in self.nodes if self._node_labels(n).get(lab)}))
+            uni_classes.setdefault(uni_labels[lab], set()).add(int(job_class[ji]))
+        uni_start = [0]
+        for vals in uni_values:
+            uni_start.append(uni_start[-1] + len(vals))
+        Vn = uni_start[-1]
+        class_uni = np.full((max(1, len(class_req)), max(1, Vn), 1 + abi.MAX_AWAY), abi.NONE, dtype=np.uint32)
+        for lab, li in uni_labels.items():
+            for c in uni_classes.get(li, ()):
+                tol, sel, aff, extras = class_meta[c]
+                for vi, val in enumerate(uni_values[li]):
+                    sel2 = dict(sel)
+                    sel2[lab] = val  # jctx.AddNodeSelector
+                    class_uni[c, uni_start[li] + vi, 0] = row_of(tol, sel2, aff)
+                    for k, extra in enumerate(extras):
+                        if extra:
+                            class_uni[c, uni_start[li] + vi, 1 + k] = row_of(tol + extra, sel2, aff)
+        self.uni_labels, self.uni_values, self.uni_start = uni_labels, uni_values, uni_start
         Cn = max(1, len(class_req))
         if not class_req:  # keep arrays non-empty for the C side
             class_req, class_pc, class_row, class_away = [np.zeros(D, np.int64)], [0], [row_of((), {}, None)], [[abi.NONE] * abi.MAX_AWAY]
@@ -572,6 +615,28 @@ class RoundInputBuilder:
         inp.job_scheduled_at_priority = self._ptr(self.job_sap, C.c_int32)
         inp.job_active_run_timestamp = self._ptr(self.job_art, C.c_int64)
         inp.gang_cardinality = self._ptr(self.gang_card, C.c_uint32)
+        gang_label = np.full(max(1, len(gang_card)), abi.NONE, dtype=np.uint32)
+        for ji, j in enumerate(self.jobs):
+            if job_gang[ji] != abi.NONE and j.gang_node_uniformity_label:
+                lab = j.gang_node_uniformity_label
+                gang_label[job_gang[ji]] = self.uni_labels[lab] if lab in indexed_labels else abi.LABEL_NOT_INDEXED
+        self.gang_label = a(gang_label, np.uint32)
+        self.uni_start_arr = a(self.uni_start, np.uint32)
+        self.class_uni = a(class_uni, np.uint32)
+        if (gang_label != abi.NONE).any():
+            inp.gang_uniformity_label = self._ptr(self.gang_label, C.c_uint32)
+            inp.num_uniformity_labels = len(self.uni_values)
+            inp.uniformity_value_start = self._ptr(self.uni_start_arr, C.c_uint32)
+            inp.class_uniformity_row = self._ptr(self.class_uni, C.c_uint32)
+        # floating resources (floatingresources/floating_resource_types.go:19-37)
+        fmask = 0
+        for fr in cfg.floating_resources:
+            d = f.index[fr.name]
+            fmask |= 1 << d
+            if fr.quantity is not None:
+                inp.floating_limits_configured = 1
+                inp.floating_limit[d] = f.scaled_value(fr.name, fr.quantity)
+        inp.floating_resource_mask = fmask
 
         # ---- scheduling context scalars ----
         if total_resources is None:  # nodeDb.TotalKubernetesResources(): Σ allocatable

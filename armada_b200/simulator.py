@@ -19,9 +19,8 @@ zero-padded counters (the reference's ULIDs sort by creation time, these do too)
 are visited in name order (the reference ranges over a Go map); the shifted-exponential tails use a
 PCG64 stream seeded with WorkloadSpec.randomSeed (the reference uses math/rand — a run with
 tailMean = 0 everywhere is comparable row for row, others in distribution only).  Gang jobs carry the
-reference's default node-uniformity label (the cluster name, simulator.go:456-462): with one cluster
-per pool that selector matches every node, so such gangs are scheduled as plain gangs; a pool made
-of several clusters with gang templates is refused (`UnsupportedSpec`).
+template's node-uniformity label, by default the cluster name (simulator.go:456-462): a gang lands
+on ONE cluster of its pool (the round's node-uniformity search, gang_scheduler.go:154-223).
 """
 from __future__ import annotations
 
@@ -478,9 +477,6 @@ class Simulator:
                     self.nodes_by_pool.setdefault(c.pool, []).append(NodeSpec(nid, index, dict(t.total_resources), t.taints, labels))
                     self.pool_of_node[nid] = c.pool
                     index += 1
-        has_gangs = any(t.gang_cardinality for q in self.workload_spec.queues for t in q.job_templates)
-        if has_gangs and any(n > 1 for n in clusters_of_pool.values()):
-            raise UnsupportedSpec("gang templates over a pool of several clusters need the node-uniformity search")
         labels = list(self.cfg.indexed_node_labels)
         if CLUSTER_LABEL not in labels:
             self.cfg.indexed_node_labels = tuple(labels + [CLUSTER_LABEL])
@@ -549,7 +545,8 @@ class Simulator:
         t = j.template
         return JobSpec(id=j.id, queue=j.queue, priority_class=t.priority_class_name or self.default_pc, requests=t.requests,
                        queue_priority=t.queue_priority, submit_time=j.created, tolerations=t.tolerations, node_selector=t.node_selector,
-                       gang_id=j.gang_id, gang_cardinality=t.gang_cardinality if j.gang_id else 1, node=j.node,
+                       gang_id=j.gang_id, gang_cardinality=t.gang_cardinality if j.gang_id else 1,
+                       gang_node_uniformity_label=(t.gang_node_uniformity_label or CLUSTER_LABEL) if j.gang_id else None, node=j.node,
                        scheduled_at_priority=j.scheduled_at_priority, active_run_timestamp=j.run_created)
 
     def _handle_schedule(self):

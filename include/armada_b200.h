@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ARMADA_ABI_VERSION 1u
+#define ARMADA_ABI_VERSION 2u
 
 #define ARMADA_MAX_RESOURCES 8u
 #define ARMADA_MAX_PRIORITIES 16u
@@ -44,6 +44,7 @@ extern "C" {
 #define ARMADA_MAX_AWAY 4u
 #define ARMADA_NONE 0xFFFFFFFFu /* "no node" / "no gang" / "no queue" / "no row" */
 #define ARMADA_NO_PRIORITY INT32_MIN
+#define ARMADA_LABEL_NOT_INDEXED 0xFFFFFFFEu /* gang_uniformity_label: label set on the gang but not indexed */
 
 /* ---- status codes (never abort/panic; 0 = OK) ------------------------------------- */
 enum {
@@ -97,7 +98,12 @@ enum {
   ARMADA_REASON_GANG_EXCEEDS_QUEUE_BURST = 9,
   ARMADA_REASON_GANG_DOES_NOT_FIT = 10,
   ARMADA_REASON_JOB_DOES_NOT_FIT = 11,
-  ARMADA_REASON_NO_REMAINING_CANDIDATES = 12     /* termination only */
+  ARMADA_REASON_NO_REMAINING_CANDIDATES = 12,    /* termination only */
+  /* GangScheduler.trySchedule / IsWithinFloatingResourceLimits (gang_scheduler.go:143,154-223) */
+  ARMADA_REASON_UNIFORMITY_LABEL_NOT_INDEXED = 13,   /* "uniformity label %s is not indexed"            */
+  ARMADA_REASON_NO_NODES_WITH_UNIFORMITY_LABEL = 14, /* "no nodes with uniformity label %s"             */
+  ARMADA_REASON_GANG_FITS_NO_UNIFORMITY_VALUE = 15,  /* "at least one job in the gang does not fit on any node" */
+  ARMADA_REASON_FLOATING_RESOURCES = 16              /* floating resources not configured / exceeded    */
 };
 
 /* kinds of ArmadaRoundOutput.job_excluded_nodes */
@@ -221,6 +227,30 @@ typedef struct {
    * SchedulingOrderCompare (jobdb/comparison.go:49-107). */
   const uint32_t* queued_start;      /* [Q+1] or NULL */
   const uint32_t* queued_order;      /* [#queued] job indices, or NULL */
+  /* ---- ABI 2: gang node uniformity (gang_scheduler.go:154-223) ------------------------------------
+     A gang with a NodeUniformityLabel is tried once per distinct non-empty value of that label among the
+     nodes (the label's value slots, in string order — the reference ranges over a Go map, so among equally
+     good values ITS choice is random; this library's is the first in string order), every member with the
+     selector label=value added; the best fit wins (context/gang.go:82-110).  The host supplies, per job
+     class and value slot, the static rows of the class with that selector added.  NULL
+     gang_uniformity_label: no gang has one. */
+  const uint32_t* gang_uniformity_label;  /* [G] dense label id < L, ARMADA_NONE = the gang has none,
+                                             ARMADA_LABEL_NOT_INDEXED = set but not in IndexedNodeLabels   */
+  uint32_t num_uniformity_labels;         /* L */
+  uint32_t _pad_uniformity;
+  const uint32_t* uniformity_value_start; /* [L+1] label l owns value slots [start[l], start[l+1]); an empty
+                                             range = "no nodes with uniformity label"                       */
+  const uint32_t* class_uniformity_row;   /* [C][V][1 + ARMADA_MAX_AWAY], V = start[L]: bitmap row of the class
+                                             with the selector of value slot v added — [0] as submitted, [1+k]
+                                             with the away tolerations k; ARMADA_NONE where class_away_row[k] is,
+                                             or where no gang of this class carries that label               */
+  /* ---- ABI 2: floating resources (floatingresources/floating_resource_types.go:60-72,
+     context/scheduling.go:493-517).  A floating resource is a dimension of class_request that no node
+     holds: it counts in the queue accounting and DRF, never in the node fit. */
+  uint32_t floating_resource_mask;        /* bit d ⇒ resource d is a floating resource                  */
+  uint8_t floating_limits_configured;     /* FloatingResourceTypes knows this pool                      */
+  uint8_t _pad_floating[3];
+  int64_t floating_limit[ARMADA_MAX_RESOURCES]; /* the pool's totals of the floating resources          */
 } ArmadaRoundInput;
 
 /* All arrays are caller-allocated; any pointer may be NULL to skip that output. */

@@ -182,11 +182,30 @@ struct NodeDb {
       for (int d = 0; d < D; ++d)
         for (uint32_t n = 0; n < N; ++n) A(p, d, n) = in->node_allocatable[(size_t)d * N + n];
     for (uint32_t n = 0; n < N; ++n) insert_keys(n);
+    // KubernetesResourceRequirements = AllResourceRequirements without the floating resources (job.go):
+    // what the NodeDb compares with and books on nodes
+    node_req.assign(in->class_request, in->class_request + (size_t)in->num_classes * D);
+    for (uint32_t c = 0; c < in->num_classes; ++c)
+      for (int d = 0; d < D; ++d)
+        if ((in->floating_resource_mask >> d) & 1u) node_req[(size_t)c * D + d] = 0;
   }
 
   int64_t& A(int p, int d, uint32_t n) { return alloc[((size_t)p * D + d) * N + n]; }
   int64_t total(int d, uint32_t n) const { return in->node_total[(size_t)d * N + n]; }
-  const int64_t* req_of(uint32_t job) const { return in->class_request + (size_t)in->job_class[job] * D; }
+  std::vector<int64_t> node_req;  // [C][D]
+  const int64_t* req_of(uint32_t job) const { return node_req.data() + (size_t)in->job_class[job] * D; }
+  // gang node uniformity (gang_scheduler.go:191): while >= 0, every jctx carries the node selector of this value
+  // slot — the static rows come from class_uniformity_row instead of class_static_row / class_away_row
+  int64_t uniformity_slot = -1;
+  uint32_t base_row(uint32_t c) const {
+    if (uniformity_slot < 0) return in->class_static_row[c];
+    return in->class_uniformity_row[((size_t)c * uniformity_V() + (size_t)uniformity_slot) * (1 + ARMADA_MAX_AWAY)];
+  }
+  uint32_t away_row(uint32_t c, uint32_t k) const {
+    if (uniformity_slot < 0) return in->class_away_row[(size_t)c * ARMADA_MAX_AWAY + k];
+    return in->class_uniformity_row[((size_t)c * uniformity_V() + (size_t)uniformity_slot) * (1 + ARMADA_MAX_AWAY) + 1 + k];
+  }
+  size_t uniformity_V() const { return in->uniformity_value_start ? in->uniformity_value_start[in->num_uniformity_labels] : 0; }
   const ArmadaPriorityClass& pc_of(uint32_t job) const {
     return in->priority_classes[in->class_pc[in->job_class[job]]];
   }
@@ -754,7 +773,7 @@ struct NodeDb {
       uint32_t c = in->job_class[jc.job];
       for (uint32_t k = 0; k < pc.num_away; ++k) {
         // selectNodeForJobWithTxnAndAwayNodeType, nodedb.go:559-603
-        uint32_t away_row = in->class_away_row[(size_t)c * ARMADA_MAX_AWAY + k];
+        uint32_t away_row = this->away_row(c, k);
         if (away_row == NONE) continue;  // "No extra taints to tolerate"
         uint32_t saved_row = jc.row;
         bool saved_additional = jc.has_additional;
@@ -881,7 +900,7 @@ struct Round {
     build_queued_order();
   }
 
-  const int64_t* req_of(uint32_t job) const { return db.req_of(job); }
+  const int64_t* req_of(uint32_t job) const { return in->class_request + (size_t)in->job_class[job] * D; }  // AllResourceRequirements
   uint32_t pc_index(uint32_t job) const { return in->class_pc[in->job_class[job]]; }
 
   // Snapshot construction when the caller leaves the queue accounting to the library (NULL
@@ -1168,6 +1187,96 @@ struct Round {
     return g;
   }
 
+  // sctx.IsWithinFloatingResourceLimits (context/scheduling.go:493-517) + FloatingResourceTypes.WithinLimits
+  // (floatingresources/floating_resource_types.go:60-72).  sctx.Allocated = the sum of the queues' allocations,
+  // this gang included (AddGangSchedulingContext ran).  Jobs of other pools ("away" in the cross-pool sense) are
+  // not expressible in the ABI.
+  uint8_t check_floating_resources(const Gang& g) const {
+    if (!in->floating_resource_mask) return ARMADA_REASON_NONE;
+    bool requests = false;
+    for (JobCtx* jc : g.jctxs) {
+      const int64_t* r = req_of(jc->job);
+      for (int d = 0; d < D; ++d)
+        if (((in->floating_resource_mask >> d) & 1u) && r[d] > 0) requests = true;
+    }
+    if (!requests) return ARMADA_REASON_NONE;
+    if (!in->floating_limits_configured) return ARMADA_REASON_FLOATING_RESOURCES;
+    for (int d = 0; d < D; ++d) {
+      if (!((in->floating_resource_mask >> d) & 1u)) continue;
+      int64_t a = 0;
+      for (uint32_t q = 0; q < Q; ++q) a += qctx[q].allocated[d];
+      if (a > in->floating_limit[d]) return ARMADA_REASON_FLOATING_RESOURCES;
+    }
+    return ARMADA_REASON_NONE;
+  }
+  // tryScheduleGang (gang_scheduler.go:225-238)
+  bool try_schedule_gang(Gang& g, uint8_t* reason) {
+    db.begin();
+    bool ok = db.schedule_many(g.jctxs);
+    if (ok) {
+      db.commit();
+    } else {
+      db.abort();
+      *reason = g.jctxs.size() > 1 ? ARMADA_REASON_GANG_DOES_NOT_FIT : ARMADA_REASON_JOB_DOES_NOT_FIT;
+    }
+    return ok;
+  }
+  void set_uniformity_slot(Gang& g, int64_t slot) {  // addNodeSelectorToGctx (:256-260)
+    db.uniformity_slot = slot;
+    for (JobCtx* jc : g.jctxs) {
+      jc->row = db.base_row(in->job_class[jc->job]);
+      if (slot >= 0) jc->has_additional = true;
+    }
+  }
+  // trySchedule (gang_scheduler.go:150-223): one attempt per value of the gang's node-uniformity label, each in a
+  // transaction that is rolled back unless it is the best possible fit; the best value is then scheduled for real.
+  // Values are tried in slot (string) order — the reference ranges over a Go map.
+  bool try_schedule(Gang& g, uint8_t* reason) {
+    const uint32_t gi = in->job_gang[g.jctxs[0]->job];
+    const uint32_t label = (g.jctxs.size() > 1 && gi != NONE && in->gang_uniformity_label) ? in->gang_uniformity_label[gi] : NONE;
+    if (label == NONE) return try_schedule_gang(g, reason);
+    if (label == ARMADA_LABEL_NOT_INDEXED) {
+      *reason = ARMADA_REASON_UNIFORMITY_LABEL_NOT_INDEXED;
+      return false;
+    }
+    const uint32_t v0 = in->uniformity_value_start[label], v1 = in->uniformity_value_start[label + 1];
+    if (v0 == v1) {
+      *reason = ARMADA_REASON_NO_NODES_WITH_UNIFORMITY_LABEL;
+      return false;
+    }
+    int64_t best = -1;
+    double best_mean = 0;  // GangSchedulingFit (context/gang.go:82-110): every attempt that succeeds places the whole gang
+    for (uint32_t v = v0; v < v1; ++v) {
+      set_uniformity_slot(g, v);
+      db.begin();
+      const bool ok = db.schedule_many(g.jctxs);
+      if (ok) {
+        int32_t total = 0;
+        for (JobCtx* jc : g.jctxs) total += jc->p_preempted_at;
+        const double mean = (double)total / (double)g.jctxs.size();
+        if (mean == (double)MIN_PRIORITY || ((best < 0 || best_mean > mean) && v + 1 == v1)) {
+          db.commit();  // best possible, or the best so far with nothing left to try
+          db.uniformity_slot = -1;
+          return true;
+        }
+        if (best < 0 || best_mean > mean) {
+          best = v;
+          best_mean = mean;
+        }
+      }
+      db.abort();
+    }
+    if (best < 0) {
+      set_uniformity_slot(g, -1);
+      *reason = ARMADA_REASON_GANG_FITS_NO_UNIFORMITY_VALUE;
+      return false;
+    }
+    set_uniformity_slot(g, best);
+    const bool ok = try_schedule_gang(g, reason);
+    db.uniformity_slot = -1;
+    return ok;
+  }
+
   bool gang_schedule(Gang& g, bool skip_key_check, uint8_t* reason_out) {
     uint8_t reason = ARMADA_REASON_NONE;
     bool ok = true;
@@ -1187,17 +1296,10 @@ struct Round {
       if (reason != ARMADA_REASON_NONE) ok = false;
     }
     if (ok) {
-      // trySchedule → tryScheduleGang → tryScheduleGangWithTxn (:150-254).  Node-uniformity
-      // label search (:175-223) is not modelled (host must not set it).
-      db.begin();
-      ok = db.schedule_many(g.jctxs);
-      if (ok) {
-        db.commit();
-      } else {
-        db.abort();
-        reason = g.jctxs.size() > 1 ? ARMADA_REASON_GANG_DOES_NOT_FIT : ARMADA_REASON_JOB_DOES_NOT_FIT;
-      }
+      reason = check_floating_resources(g);  // IsWithinFloatingResourceLimits (:143)
+      if (reason != ARMADA_REASON_NONE) ok = false;
     }
+    if (ok) ok = try_schedule(g, &reason);
     if (ok) {
       if (!g.all_evicted) {  // Limiter.ReserveN (:118-123)
         if (!in->global_limiter_is_inf) global_tokens -= (double)g.jctxs.size();

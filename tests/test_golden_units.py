@@ -8,6 +8,8 @@
 import ctypes as C
 from fractions import Fraction
 
+import json
+
 import numpy as np
 import pytest
 
@@ -129,47 +131,11 @@ def _single_queue(gangs):
 def test_gang_scheduler(name):
     """TestGangScheduler cases whose gangs all belong to one queue are order-equivalent to a
     QueueScheduler pass over that queue (gangs in submit order), so they can be driven through the
-    round entry point."""
-    env = gt.Env()
-    env.calls["testfixtures.WithNodeUniformityGangAnnotationsJobs"] = lambda jobs, label: (_ for _ in ()).throw(gt.UnsupportedCase("node uniformity"))
-    try:
-        tc = env.ev(GANG[name])
-    except gt.UnsupportedCase as e:
-        pytest.skip(f"not modelled: {e}")
-    gangs = tc["Gangs"]
-    if not _single_queue(gangs):
-        pytest.skip("multi-queue gang case: direct GangScheduler order differs from queue order")
-    if tc.get("AddAwayQueueContexts"):
-        pytest.skip("away queue contexts")
-    cfg = tc["SchedulingConfig"]
-    nodes = tc["Nodes"]
-    t = 0
-    jobs = []
-    for gi, g in enumerate(gangs):
-        for j in g:
-            t += 1
-            j.submit_time = t
-            if len(g) == 1:
-                j.gang_id, j.gang_cardinality = None, 1
-            jobs.append(j)
-    try:
-        synth = gt.materialize_used(cfg, nodes, env.fx)
-    except gt.UnsupportedCase as e:
-        pytest.skip(str(e))
-    qname = jobs[0].queue
-    b = RoundInputBuilder(cfg, nodes, jobs + synth, [QueueSpec(qname, 1.0)])
+    round entry point (tests/gang_cases.py builds the round)."""
+    import gang_cases
+    b, tc, gangs = gang_cases.gang_case_round(name)
     res = oracle_lib.round_schedule(b.input)
-    got = []
-    for gi, g in enumerate(gangs):
-        st = [int(res.job_state[b.job_pos[j.id]]) for j in g]
-        if all(s == abi.JOB_SCHEDULED for s in st):
-            got.append(gi)
-        else:
-            assert all(s != abi.JOB_SCHEDULED for s in st), "gang partially scheduled"
-    assert got == sorted(tc.get("ExpectedScheduledIndices") or [])
-    cum = tc.get("ExpectedCumulativeScheduledJobs")
-    if cum:
-        assert int(res.out.num_scheduled_jobs) == int(cum[-1])
+    gang_cases.check_gang_case(b, tc, gangs, res)
 
 
 def test_node_index_key_bytes():

@@ -414,3 +414,34 @@ def test_excluded_nodes_static_and_resource_kinds(seed, lane_order):
     assert _excluded_nodes_properties(inp, want) > 0
     ex = np.asarray(want.job_excluded_nodes)
     assert ex[:, abi.EXCL_STATIC].sum() > 0
+
+
+# ---- gang node uniformity + floating resources (gang_scheduler.go:143,154-223) ----------------------
+import gang_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(gang_cases.GANG.keys()))
+def test_reference_gang_scheduler_table(name):
+    """TestGangScheduler (gang_scheduler_test.go:33-760) through the kernel: node-uniformity search, floating
+    resources, round / queue limits, the resolution-rounding case."""
+    b, tc, gangs = gang_cases.gang_case_round(name)
+    got, _ = assert_parity(b.input, name)
+    gang_cases.check_gang_case(b, tc, gangs, got)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_uniformity_and_floating_rounds(seed, lane_order):
+    got, want = assert_parity(gang_cases.uniformity_round(seed).input, f"uniformity round {seed}")
+    if seed == 1:  # the generator reaches every new outcome
+        reasons = set(int(x) for x in want.job_reason)
+        assert {abi.REASON_UNIFORMITY_LABEL_NOT_INDEXED, abi.REASON_NO_NODES_WITH_UNIFORMITY_LABEL, abi.REASON_GANG_FITS_NO_UNIFORMITY_VALUE,
+                abi.REASON_FLOATING_RESOURCES} <= reasons
+
+
+@pytest.mark.parametrize("seed", [20, 21, 22])
+def test_uniformity_rounds_in_exact_mode(seed):
+    assert_parity(gang_cases.uniformity_round(seed, unaligned=True).input, f"unaligned uniformity round {seed}")
+
+
+def test_uniformity_rounds_without_floating_resources_keep_the_batch_pipeline():
+    got, _ = assert_parity(gang_cases.uniformity_round(30, n_nodes=80, n_jobs=600, floating=False).input, "uniformity, no floating")

@@ -359,3 +359,26 @@ def test_excluded_nodes_at_c3_scale():
     got, _ = assert_parity(inp, "C3@0.05 with excluded-node kinds")
     tot = np.asarray(got.job_excluded_nodes).sum(axis=1)
     assert (tot[tot > 0] == inp.num_nodes).all() and (tot > 0).any()
+
+
+# ---- gang node uniformity + floating resources (gang_scheduler.go:143,154-223) ----------------------
+import gang_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(gang_cases.GANG.keys()))
+def test_reference_gang_scheduler_table_on_device(name):
+    b, tc, gangs = gang_cases.gang_case_round(name)
+    got, _ = assert_parity(b.input, name)
+    gang_cases.check_gang_case(b, tc, gangs, got)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_uniformity_and_floating_rounds(seed):
+    assert_parity(gang_cases.uniformity_round(seed).input, f"uniformity round {seed}")
+
+
+@pytest.mark.parametrize("seed,unaligned,floating", [(40, False, False), (41, True, True), (42, False, True)])
+def test_uniformity_rounds_at_scale(seed, unaligned, floating):
+    b = gang_cases.uniformity_round(seed, n_nodes=1500, n_zones=12, n_queues=8, n_jobs=9000, floating=floating, unaligned=unaligned)
+    got, want = assert_parity(b.input, f"uniformity round {seed} at scale")
+    assert int(want.out.num_result_scheduled) > 1000

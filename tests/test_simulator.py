@@ -74,6 +74,9 @@ SCENARIOS = {
                    lambda: workload(("A", [jt32(2, "foo", fx.PriorityClass0)]), ("B", [jt32(1, "bar", fx.PriorityClass0, earliest_submit_time=30 * sim.NS)])), 5,
                    [("submit", "A", 2), ("leased", "A", 2), ("submit", "B", 1), ("preempted", "A", 1), ("leased", "B", 1), ("submit", "A", 1),
                     ("succeeded", "A", 1), ("leased", "A", 1), ("succeeded", "B", 1), ("succeeded", "A", 1)]),
+    # :441-479: Cluster2 is too small for a gang; the uniformity label (the cluster name) keeps every gang on Cluster1
+    "Gang Job": (cluster(("Cluster1", 8), ("Cluster2", 1)), lambda: workload(("A", [jt32(16, "foo", DEFAULT, gang_cardinality=8)])), 5,
+                 [("submit", "A", 16), ("leased", "A", 8), ("succeeded", "A", 8), ("leased", "A", 8), ("succeeded", "A", 8)]),
     # :480-520
     "Preempted Gang Job": (cluster(("Cluster1", 8)),
                            lambda: workload(("A", [jt32(8, "foo", fx.PriorityClass2, gang_cardinality=8)]),
@@ -93,13 +96,6 @@ def run_scenario(name, engine):
 def test_reference_scenarios(name):
     s, want = run_scenario(name, oracle_engine)
     assert summary(s) == want
-
-
-def test_gangs_over_several_clusters_are_refused():
-    """"Gang Job" (simulator_test.go:441-479) needs the node-uniformity search over cluster names."""
-    with pytest.raises(sim.UnsupportedSpec):
-        sim.Simulator(cluster(("Cluster1", 8), ("Cluster2", 1)), workload(("A", [jt32(16, "foo", DEFAULT, gang_cardinality=8)])),
-                      fx.test_scheduling_config(), engine=oracle_engine)
 
 
 def test_yaml_specs_and_c1(tmp_path):
@@ -147,7 +143,7 @@ def test_duration_and_spec_parsing():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["Preemption", "Preempted Gang Job", "10 jobs in sequence"])
+@pytest.mark.parametrize("name", ["Preemption", "Preempted Gang Job", "Gang Job", "10 jobs in sequence"])
 def test_reference_scenarios_on_the_device(name):
     s, want = run_scenario(name, sim.device_engine(0))
     assert summary(s) == want
