@@ -633,7 +633,7 @@ class Simulator:
                     cost = max(cost, float(res.queue_allocated[qi, d]) / totals[d] * drf_mult[d])
             rows.append(QueueStatsRow(
                 ts=self.time // NS, queue=q.name, pool=pool, fair_share=float(res.queue_fair_share[qi, 0]),
-                adjusted_fair_share=float(res.queue_fair_share[qi, 1]), actual_share=cost, cpu_share=share(qi, "cpu"),
+                adjusted_fair_share=float(res.queue_fair_share[qi, 1]), actual_share=float(cost), cpu_share=share(qi, "cpu"),
                 memory_share=share(qi, "memory"), gpu_share=share(qi, "nvidia.com/gpu"), allocated_cpu=units(qi, "cpu"),
                 allocated_memory=units(qi, "memory") // (1024 * 1024), allocated_gpu=units(qi, "nvidia.com/gpu"),
                 num_scheduled=sum(1 for i in mine if state[i] in (abi.JOB_SCHEDULED, abi.JOB_SCHEDULED_AND_EVICTED)),

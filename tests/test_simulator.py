@@ -156,5 +156,5 @@ def test_c1_on_the_device_matches_the_oracle_driven_run():
     ref = sim.simulate_files(*args, engine=oracle_engine)
     assert dev.rounds == ref.rounds and dev.rounds > 13
     assert dev.sink.job_rows == ref.sink.job_rows
-    assert dev.sink.queue_rows == ref.sink.queue_rows
+    assert repr(dev.sink.queue_rows) == repr(ref.sink.queue_rows)  # (gpu_share is NaN = 0/0 like the reference's: compare the text)
     assert dev.transitions == ref.transitions
