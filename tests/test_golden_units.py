@@ -262,3 +262,13 @@ def test_schedule_many(name):
         if ok:
             assert (node != abi.NONE).all()
     assert got == want
+
+
+import order_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(order_cases.CASES))
+def test_job_priority_comparer(name):
+    """TestJobPriorityComparer (jobdb/comparison_test.go:13-75) through the round's attempt order."""
+    b, expected = order_cases.comparison_round(name)
+    order_cases.check_order(b, expected, oracle_lib.round_schedule(b.input))

@@ -445,3 +445,13 @@ def test_uniformity_rounds_in_exact_mode(seed):
 
 def test_uniformity_rounds_without_floating_resources_keep_the_batch_pipeline():
     got, _ = assert_parity(gang_cases.uniformity_round(30, n_nodes=80, n_jobs=600, floating=False).input, "uniformity, no floating")
+
+
+import order_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(order_cases.CASES))
+def test_job_priority_comparer(name):
+    b, expected = order_cases.comparison_round(name)
+    got, _ = assert_parity(b.input, name)
+    order_cases.check_order(b, expected, got)

@@ -382,3 +382,13 @@ def test_uniformity_rounds_at_scale(seed, unaligned, floating):
     b = gang_cases.uniformity_round(seed, n_nodes=1500, n_zones=12, n_queues=8, n_jobs=9000, floating=floating, unaligned=unaligned)
     got, want = assert_parity(b.input, f"uniformity round {seed} at scale")
     assert int(want.out.num_result_scheduled) > 1000
+
+
+import order_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(order_cases.CASES))
+def test_job_priority_comparer_on_device(name):
+    b, expected = order_cases.comparison_round(name)
+    got, _ = assert_parity(b.input, name)
+    order_cases.check_order(b, expected, got)
