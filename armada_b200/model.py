@@ -29,9 +29,9 @@ NODE_ID_LABEL = "armadaproject.io/nodeId"
 WILDCARD = "*"  # configuration.WildCardWellKnownNodeTypeValue
 
 _SUFFIX = {
-    "": Fraction(1), "m": Fraction(1, 1000), "k": Fraction(10**3), "M": Fraction(10**6), "G": Fraction(10**9),
+    "": Fraction(1), "n": Fraction(1, 10**9), "u": Fraction(1, 10**6), "m": Fraction(1, 1000), "k": Fraction(10**3), "M": Fraction(10**6), "G": Fraction(10**9),
     "T": Fraction(10**12), "P": Fraction(10**15), "Ki": Fraction(2**10), "Mi": Fraction(2**20),
-    "Gi": Fraction(2**30), "Ti": Fraction(2**40), "Pi": Fraction(2**50),
+    "Gi": Fraction(2**30), "Ti": Fraction(2**40), "Pi": Fraction(2**50), "Ei": Fraction(2**60), "E": Fraction(10**18),
 }
 
 
@@ -40,7 +40,7 @@ def parse_quantity(q) -> Fraction:
     if isinstance(q, (int, Fraction)):
         return Fraction(q)
     s = str(q).strip()
-    for suf in ("Ki", "Mi", "Gi", "Ti", "Pi", "m", "k", "M", "G", "T", "P"):
+    for suf in ("Ki", "Mi", "Gi", "Ti", "Pi", "Ei", "n", "u", "m", "k", "M", "G", "T", "P", "E"):
         if s.endswith(suf):
             return Fraction(s[: -len(suf)]) * _SUFFIX[suf]
     return Fraction(s)

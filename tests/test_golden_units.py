@@ -272,3 +272,28 @@ def test_job_priority_comparer(name):
     """TestJobPriorityComparer (jobdb/comparison_test.go:13-75) through the round's attempt order."""
     b, expected = order_cases.comparison_round(name)
     order_cases.check_order(b, expected, oracle_lib.round_schedule(b.input))
+
+
+@pytest.mark.parametrize("name,pc_fraction,queue_fraction,want", [
+    # constraints_test.go:53-63, :96-111, :131-140, :141-150 — pool total 1000 cpu / 1000Gi
+    ("within-constraints", {"cpu": 0.9, "memory": 0.9}, {"cpu": 0.9, "memory": 0.9}, ("900", "900Gi")),
+    ("exceeds-queue-priority-class-constraint", {}, {"cpu": 0.000001, "memory": 0.9}, ("1m", "900Gi")),
+    ("exceeds-priority-class-constraint", {"cpu": 0.00000001, "memory": 0.9}, None, ("10n", "900Gi")),
+    ("priority-class-constraint-ignored-if-there-is-a-queue-constraint", {"cpu": 0.00000001, "memory": 0.9}, {"cpu": 0.9, "memory": 0.9}, ("900", "900Gi")),
+    ("no-constraints", {}, None, None),
+])
+def test_per_queue_limits(name, pc_fraction, queue_fraction, want):
+    """TestConstraints' GetQueueResourceLimit expectations (constraints_test.go:32-178): calculatePerQueueLimits
+    (constraints.go:231-256) as flattened by RoundInputBuilder into queue_limit[Q][PC][D]."""
+    cfg = SchedulingConfig(supported_resource_types=[ResourceType("cpu", "1m"), ResourceType("memory", "1")],
+                           indexed_resources=[ResourceType("cpu", "1"), ResourceType("memory", "1")],
+                           priority_classes={"priority-class-1": PriorityClass(0, True, (), dict(pc_fraction))}, drf_resources=["cpu", "memory"])
+    q = QueueSpec("queue-1", 1.0, resource_limits_by_pc={"priority-class-1": queue_fraction} if queue_fraction is not None else {})
+    f = cfg.factory()
+    total = f.from_node({"cpu": "1000", "memory": "1000Gi"})
+    b = RoundInputBuilder(cfg, [], [], [q], total_resources=total)
+    got = b.ql[0, 0]
+    if want is None:  # rlFactory.MakeAllMax()
+        assert (got == 2**63 - 1).all()
+    else:
+        assert list(got) == list(f.from_node({"cpu": want[0], "memory": want[1]}))
