@@ -177,6 +177,9 @@ struct DevPtrs {
   uint32_t* fp_epoch;              // [N]
   uint32_t* fp_head;               // [N] most recent visited evicted index on the node
   uint32_t* fp_next;               // [J] chain by evicted index
+  uint32_t* nl_start;              // [N+1] node n's evicted jobs = nl_item[nl_start[n] .. nl_start[n+1]) (built after the indices are assigned)
+  uint2* nl_item;                  // [E] {evicted index | alive << 31, job class}, per node by descending index
+  uint32_t* nl_pos;                // [E] position of evicted index i in nl_item (NONE: the job sits on no node)
   uint32_t* nver;                  // [N] changes of the node's rows / evicted jobs so far (trigger caches)
   uint32_t* fc_ver;                // [8][N] pairs {nver the cached trigger was computed at, cached fair-preemption trigger index (-1 none)}
   uint32_t* bver;                  // [ceil(N/256)] changes of any node of the 256-node block (sum of its nver)
