@@ -455,3 +455,15 @@ def test_job_priority_comparer(name):
     b, expected = order_cases.comparison_round(name)
     got, _ = assert_parity(b.input, name)
     order_cases.check_order(b, expected, got)
+
+
+def test_presorted_job_order_fast_path_equals_the_general_path(monkeypatch):
+    """armada_round_upload ranks the jobs of a queue without building sort keys when every queue already arrives in
+    SchedulingOrderCompare order (the BASELINE configs do); ARMADA_NO_PRESORTED forces the bucket sort."""
+    for name, scale in (("C3", 0.004), ("C5", 0.004), ("C4", 0.006)):
+        inp = synth.scaled(name, scale).to_input()
+        fast, want = assert_parity(inp, f"{name} presorted")
+        monkeypatch.setenv("ARMADA_NO_PRESORTED", "1")
+        general, _ = assert_parity(inp, f"{name} general order path")
+        monkeypatch.delenv("ARMADA_NO_PRESORTED")
+        assert not fast.diff(general)
