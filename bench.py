@@ -37,9 +37,16 @@ import time
 # Before anything creates the CUDA context: one hardware work queue per concurrent round (the pools
 # of a cycle run on one stream each; with the default of 8 queues two of them can share one).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version to STDOUT, in front of the one JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL prints its version banner (and, with NCCL_DEBUG set, more) to STDOUT, in front of the one JSON line the
+# contract allows there: everything any library writes to file descriptor 1 goes to stderr, and the JSON line is
+# written to the real stdout at the end (emit()).
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 import numpy as np
 
@@ -213,7 +220,7 @@ def run_reference(args):
                                    f"other => 1 of {host_cores()} host cores; Go toolchain unavailable here)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -444,7 +451,7 @@ def main():
                     except Exception as e:  # an extra workload must not take the headline down
                         extras[nm] = {"error": str(e)[:300]}
             line["extra_workloads"] = extras
-        print(json.dumps(line))
+        emit(line)
     cyc.close()
     if world > 1:
         dist.destroy_process_group()
