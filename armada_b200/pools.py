@@ -37,32 +37,61 @@ def summary_row(p: int, res) -> List[int]:
             int((np.nonzero(sched)[0].astype(np.int64) * 1000003 + node[sched]).sum() % (2**61 - 1))]
 
 
+_CLAIM_BUFFERS: dict = {}
+
+
 def gather_claims(results: dict, num_pools: int, max_jobs: int, rank: int, world: int, dist=None) -> np.ndarray:
     """Every rank ends up with claims[pool][job] = node the job was scheduled on this cycle
     (0xFFFFFFFF = not scheduled): ONE all_gather of this rank's slab of per-pool claim rows.
-    `results` maps pool index -> RoundResult for the pools this rank owns."""
+    `results` maps pool index -> RoundResult for the pools this rank owns.  The staging buffers
+    (page-locked host slabs, device slabs) are kept between cycles; with NCCL the exchange is one
+    host-to-device copy, one all_gather over NVLink and one device-to-host copy."""
     per_rank = (num_pools + world - 1) // world
-    slab = np.full((per_rank, max_jobs), 0xFFFFFFFF, dtype=np.uint32)
-    for i, p in enumerate(pools_of_rank(num_pools, rank, world)):
-        r = results[p]
+    single = dist is None or world == 1
+    nccl = (not single) and dist.get_backend() == "nccl"
+    key = (num_pools, max_jobs, rank, world, "nccl" if nccl else "host")
+    buf = _CLAIM_BUFFERS.get(key)
+    if buf is None:
+        buf = {}
+        if single:
+            buf["slab"] = np.empty((per_rank, max_jobs), dtype=np.uint32)
+        else:
+            import torch
+            buf["t_slab"] = torch.empty((per_rank, max_jobs), dtype=torch.int32, pin_memory=nccl)
+            buf["slab"] = buf["t_slab"].numpy().view(np.uint32)
+            buf["t_out"] = torch.empty((world, per_rank, max_jobs), dtype=torch.int32, pin_memory=nccl)
+            if nccl:
+                buf["d_slab"] = torch.empty((per_rank, max_jobs), dtype=torch.int32, device="cuda")
+                buf["d_out"] = torch.empty((world, per_rank, max_jobs), dtype=torch.int32, device="cuda")
+        _CLAIM_BUFFERS[key] = buf
+    slab = buf["slab"]
+    mine = pools_of_rank(num_pools, rank, world)
+    for i in range(per_rank):
+        row = slab[i]
+        if i >= len(mine):
+            row.fill(0xFFFFFFFF)
+            continue
+        r = results[mine[i]]
         node = np.asarray(r.job_node)
-        sched = np.asarray(r.job_state) == 1
-        row = np.where(sched, node, np.uint32(0xFFFFFFFF)).astype(np.uint32)
-        slab[i, : len(row)] = row
-    if dist is None or world == 1:
+        n = len(node)
+        np.copyto(row[:n], node)
+        row[:n][np.asarray(r.job_state) != 1] = 0xFFFFFFFF
+        row[n:].fill(0xFFFFFFFF)
+    if single:
         return slab[:num_pools]
     import torch
-    t = torch.from_numpy(slab.view(np.int32))
-    nccl = dist.get_backend() == "nccl"
     if nccl:
-        t = t.cuda(non_blocking=True)
-    parts = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(parts, t.contiguous())
-    out = torch.stack(parts).cpu().numpy().view(np.uint32)  # [world][per_rank][max_jobs]
-    claims = np.empty((num_pools, max_jobs), np.uint32)
-    for p in range(num_pools):
-        claims[p] = out[p % world, p // world]
-    return claims
+        buf["d_slab"].copy_(buf["t_slab"], non_blocking=True)
+        dist.all_gather_into_tensor(buf["d_out"], buf["d_slab"])
+        buf["t_out"].copy_(buf["d_out"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    else:
+        parts = [torch.empty_like(buf["t_slab"]) for _ in range(world)]
+        dist.all_gather(parts, buf["t_slab"])
+        for w, part in enumerate(parts):
+            buf["t_out"][w].copy_(part)
+    out = buf["t_out"].numpy().view(np.uint32)  # [world][per_rank][max_jobs]; pool p = i * world + w sits at out[w, i]
+    return out.transpose(1, 0, 2).reshape(per_rank * world, max_jobs)[:num_pools]
 
 
 class PoolCycle:
