@@ -363,7 +363,9 @@ def main():
     # ---- end to end: host buffers in, host buffers out, every pool of every cycle; with more than
     # one rank the cycle's claims are gathered on all ranks (one all_gather over NCCL)
     for _ in range(1):
-        cyc.schedule_cycle(results)  # untimed: the second pair of device contexts allocates its buffers
+        out = cyc.schedule_cycle(results)  # untimed: the second pair of device contexts allocates its buffers
+        if world > 1:  # … and the claims exchange its slabs and its NCCL connections
+            poolmod.gather_claims(out, P, max_jobs, rank, world, dist)
     barrier()
     e2e_s = 0.0
     e2e_placed = 0
