@@ -16,6 +16,48 @@ from armada_b200.model import FloatingResource, JobSpec, NodeSpec, QueueSpec, Ro
 GANG = gt.load_cases("gang_scheduler")
 
 
+def _away_node_types(F):
+    """"AwayNodeTypes" (gang_scheduler_test.go:415-483): config, node and jobs are built in closures there."""
+    from armada_b200.model import AwayNodeType, PriorityClass, Taint
+    ta, tb = Taint("taint-a", "true", "NoSchedule"), Taint("taint-b", "true", "NoSchedule")
+    cfg = fx.test_scheduling_config(
+        priority_classes={"armada-preemptible-away": PriorityClass(30000, True, (AwayNodeType(29000, "node-type-a"), AwayNodeType(29000, "node-type-b"))),
+                          "armada-preemptible-away-both": PriorityClass(30000, True, (AwayNodeType(29000, "node-type-ab"),))},
+        well_known_node_types={"node-type-a": (ta,), "node-type-b": (tb,), "node-type-ab": (ta, tb)})
+    node = F.gpu8()
+    node.taints = node.taints + (ta, tb)
+    jobs = [F.n_1cpu_4gi("A", "armada-preemptible-away", 1), F.n_1cpu_4gi("A", "armada-preemptible-away-both", 1)]
+    return {"SchedulingConfig": cfg, "Nodes": [node], "Gangs": jobs, "ExpectedScheduledIndices": [1], "ExpectedCumulativeScheduledJobs": [0, 1]}
+
+
+def _home_away(F):
+    """"Home-away scheduling" (gang_scheduler_test.go:484-529)."""
+    from armada_b200.model import AwayNodeType, PriorityClass, Taint
+    ta = Taint("taint-a", "true", "NoSchedule")
+    cfg = fx.test_scheduling_config(
+        priority_classes={"armada-preemptible": PriorityClass(30000, True),
+                          "armada-preemptible-away": PriorityClass(30000, True, (AwayNodeType(29000, "node-type-a"),))},
+        well_known_node_types={"node-type-a": (ta,)})
+    node = F.cpu32()
+    node.taints = node.taints + (ta,)
+    jobs = [F.n_32cpu_256gi_large_toleration("A", "armada-preemptible-away", 1), F.n_32cpu_256gi_large_toleration("A", "armada-preemptible-away", 1)]
+    return {"SchedulingConfig": cfg, "Nodes": [node], "Gangs": jobs, "ExpectedScheduledIndices": [0], "ExpectedCumulativeScheduledJobs": [1, 1]}
+
+
+def _queue_rate_limit(F):
+    """"Hitting queue constraint does not make job scheduling key unfeasible" (gang_scheduler_test.go:530-547): the per-queue
+    burst of 2 lets queue A's first gang through and stops its second; queue B is not affected.  (Two queues: whatever the
+    order the round visits them in, the scheduled set is the same.)"""
+    cfg = fx.test_scheduling_config(maximum_per_queue_scheduling_burst=2, maximum_per_queue_scheduling_rate=2.0)
+    jobs = [fx.with_gang(F.n_1cpu_4gi("A", fx.PriorityClass0, 2)), F.n_1cpu_4gi("A", fx.PriorityClass0, 1), F.n_1cpu_4gi("B", fx.PriorityClass0, 1)]
+    return {"SchedulingConfig": cfg, "Nodes": F.n_cpu32(1), "Gangs": jobs, "ExpectedScheduledIndices": [0, 2], "ExpectedCumulativeScheduledJobs": [2, 2, 3],
+            "AnyQueueOrder": True}
+
+
+MANUAL = {"AwayNodeTypes": _away_node_types, "Home-away scheduling": _home_away,
+          "Hitting queue constraint does not make job scheduling key unfeasible": _queue_rate_limit}
+
+
 def gang_case_round(name):
     """(builder, evaluated case, gangs) of one TestGangScheduler case; pytest.skip for what a round cannot express."""
     env = gt.Env()
@@ -35,7 +77,9 @@ def gang_case_round(name):
     env.calls["testfixtures.WithNodeUniformityGangAnnotationsJobs"] = with_uniformity
     env.calls["addFloatingResourceRequest"] = add_floating
     src = GANG[name]
-    if name == "floating resources":
+    if name in MANUAL:
+        tc = MANUAL[name](env.fx)
+    elif name == "floating resources":
         # the table builds this config in a closure (gang_scheduler_test.go:104-108): TestSchedulingConfig with
         # FloatingResources = TestFloatingResourceConfig (testfixtures.go:65-75: 10 of test-floating-resource in "pool")
         src = json.loads(json.dumps(src))
@@ -48,7 +92,7 @@ def gang_case_round(name):
         except gt.UnsupportedCase as e:
             pytest.skip(f"not modelled: {e}")
     gangs = tc["Gangs"]
-    if len({j.queue for g in gangs for j in g}) != 1:
+    if len({j.queue for g in gangs for j in g}) != 1 and not tc.get("AnyQueueOrder"):
         pytest.skip("multi-queue gang case: direct GangScheduler order differs from queue order")
     if tc.get("AddAwayQueueContexts"):
         pytest.skip("away queue contexts")
@@ -67,7 +111,7 @@ def gang_case_round(name):
         synth = gt.materialize_used(cfg, nodes, env.fx)
     except gt.UnsupportedCase as e:
         pytest.skip(str(e))
-    b = RoundInputBuilder(cfg, nodes, jobs + synth, [QueueSpec(jobs[0].queue, 1.0)])
+    b = RoundInputBuilder(cfg, nodes, jobs + synth, [QueueSpec(q, 1.0) for q in sorted({j.queue for j in jobs})])
     return b, tc, gangs
 
 
