@@ -328,7 +328,7 @@ class RoundInputBuilder:
         away = pc.away_node_types[k]
         taints: List[Taint] = []
         if away.well_known_node_type:
-            taints += list(self.cfg.well_known_node_types[away.well_known_node_type])
+            taints += list(self.cfg.well_known_node_types.get(away.well_known_node_type, ()))
         for name, conditions in away.node_types:
             ok = True
             for (resource, op, value) in conditions:  # matchesCondition :514-530 (first condition decides)
@@ -377,7 +377,8 @@ class RoundInputBuilder:
             s.num_away = len(pc.away_node_types)
             for k, a in enumerate(pc.away_node_types):
                 s.away_priority[k] = a.priority
-                s.away_well_known[k] = well_known_names.index(a.well_known_node_type) if a.well_known_node_type else abi.NONE
+                # (a name without a WellKnownNodeTypes entry adds no taints here; the reference fails the away attempt that reaches it)
+                s.away_well_known[k] = well_known_names.index(a.well_known_node_type) if a.well_known_node_type in well_known_names else abi.NONE
 
         # ---- nodes ----
         N = len(self.nodes)

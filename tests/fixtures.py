@@ -16,10 +16,10 @@ PriorityClass1 = "priority-1"
 PriorityClass2 = "priority-2"
 PriorityClass2NonPreemptible = "priority-2-non-preemptible"
 PriorityClass3 = "priority-3"
-PriorityClass4PreemptibleAway = "priority-4-preemptible-away"
-PriorityClass5PreemptibleAwayLowPriority = "priority-5-preemptible-away-low-priority"
-PriorityClass6Preemptible = "priority-6-preemptible"
-PriorityClass7PreemptibleAwayConditional = "priority-7-preemptible-away-conditional"
+PriorityClass4PreemptibleAway = "armada-preemptible-away"  # the reference's names (testfixtures.go:50-58)
+PriorityClass5PreemptibleAwayLowPriority = "armada-preemptible-away-lower"
+PriorityClass6Preemptible = "armada-preemptible"
+PriorityClass7PreemptibleAwayConditional = "armada-preemptible-away-conditional"
 
 TestHostnameLabel = "kubernetes.io/hostname"
 ClusterNameLabel = "cluster"

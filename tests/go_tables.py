@@ -13,7 +13,7 @@ import numpy as np
 
 import fixtures as fx
 from armada_b200 import abi
-from armada_b200.model import (JobSpec, MatchExpression, NodeSpec, PriorityClass, QueueSpec, ResourceType,
+from armada_b200.model import (AwayNodeType, JobSpec, MatchExpression, NodeSpec, PriorityClass, QueueSpec, ResourceType,
                                RoundInputBuilder, SchedulingConfig, Taint, Toleration, parse_quantity)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -25,7 +25,12 @@ class UnsupportedCase(Exception):
 
 def load_cases(name: str) -> Dict[str, dict]:
     with open(os.path.join(GOLDEN, f"{name}.json")) as f:
-        return json.load(f)["cases"]
+        cases = json.load(f)["cases"]
+    if name == "preempting_queue_scheduler":
+        for manual in MANUAL_PQS:
+            assert manual in cases, manual
+            cases[manual] = {"manual": manual}
+    return cases
 
 
 class Rl(dict):
@@ -322,9 +327,67 @@ def run_queue_scheduler_case(case: dict, run_round: Callable) -> None:
 # =================================================================================================
 # TestPreemptingQueueScheduler driver (preempting_queue_scheduler_test.go:2046-2377)
 # =================================================================================================
+def _gpu_taint():
+    return Taint("gpu", "true", "NoSchedule")
+
+
+def _home_away_cfg(lower: bool = False, **kw) -> SchedulingConfig:
+    pcs = {"armada-preemptible-away": PriorityClass(30000, True, (AwayNodeType(29000, "gpu"),)), "armada-preemptible": PriorityClass(30000, True)}
+    if lower:
+        pcs["armada-preemptible-away-lower"] = PriorityClass(30000, True, (AwayNodeType(28000, "gpu"),))
+    return fx.test_scheduling_config(priority_classes=pcs, well_known_node_types={"gpu": (_gpu_taint(),)}, **kw)
+
+
+def _away_jobs(F, queue, n, pc="armada-preemptible-away"):
+    return F.n_1cpu_4gi(queue, pc, n)
+
+
+def _home_gpu_jobs(F, queue, n):  # Test1GpuPodReqs + the gpu toleration, priority class armada-preemptible
+    return F.n_1gpu(queue, "armada-preemptible", n)
+
+
+def _pqs_away_first(F, mixed):
+    nodes = (F.n_cpu32(1) + [F.gpu8_tainted()]) if mixed else [F.gpu8_tainted(), F.gpu8_tainted()]
+    return {"SchedulingConfig": _home_away_cfg() if mixed else fx.test_scheduling_config(well_known_node_types={"gpu": (_gpu_taint(),)}),
+            "Nodes": nodes, "PriorityFactorByQueue": {"A": 1.0, "B": 1.0},
+            "Rounds": [{"JobsByQueue": {"A": _away_jobs(F, "A", 96)}, "ExpectedScheduledIndices": {"A": list(range(96))}},
+                       {"JobsByQueue": {"B": _home_gpu_jobs(F, "B", 12)}, "ExpectedScheduledIndices": {"B": list(range(8 if mixed else 12))},
+                        "ExpectedPreemptedIndices": {"A": {0: list(range(32, 96))}}}]}
+
+
+def _pqs_home_first(F, mixed):
+    nodes = (F.n_cpu32(1) + [F.gpu8_tainted()]) if mixed else [F.gpu8_tainted(), F.gpu8_tainted()]
+    return {"SchedulingConfig": _home_away_cfg(), "Nodes": nodes, "PriorityFactorByQueue": {"A": 1.0, "B": 1.0},
+            "Rounds": [{"JobsByQueue": {"B": _home_gpu_jobs(F, "B", 12)}, "ExpectedScheduledIndices": {"B": list(range(8 if mixed else 12))}},
+                       {"JobsByQueue": {"A": _away_jobs(F, "A", 96)}, "ExpectedScheduledIndices": {"A": list(range(32))}}]}
+
+
+def _pqs_multiple_levels(F):
+    node = F.cpu32()
+    node.taints = node.taints + (_gpu_taint(),)
+    c_jobs = F.n_jobs("C", "armada-preemptible", 17, {"cpu": "1", "memory": "4Gi"}, (Toleration("gpu", "", "true"),))
+    return {"SchedulingConfig": _home_away_cfg(lower=True, protected_fraction_of_fair_share=5.0), "Nodes": [node],
+            "PriorityFactorByQueue": {"A": 1.0, "B": 1.0, "C": 1.0},
+            "Rounds": [{"JobsByQueue": {"A": _away_jobs(F, "A", 16, "armada-preemptible-away-lower"), "B": _away_jobs(F, "B", 16)},
+                        "ExpectedScheduledIndices": {"A": list(range(16)), "B": list(range(16))}},
+                       {"JobsByQueue": {"C": c_jobs}, "ExpectedScheduledIndices": {"C": list(range(17))},
+                        "ExpectedPreemptedIndices": {"A": {0: list(range(16))}, "B": {0: [15]}}}]}
+
+
+# TestPreemptingQueueScheduler cases whose config / nodes / jobs are built in closures in the table
+# (preempting_queue_scheduler_test.go:1707-2045): transcribed by hand
+MANUAL_PQS = {
+    "home-away preemption, away jobs first": lambda F: _pqs_away_first(F, False),
+    "home-away preemption, home jobs first": lambda F: _pqs_home_first(F, False),
+    "home-away preemption, mixed nodes, away jobs first": lambda F: _pqs_away_first(F, True),
+    "home-away preemption, mixed nodes, home jobs first": lambda F: _pqs_home_first(F, True),
+    "home-away preemption through multiple levels": _pqs_multiple_levels,
+}
+
+
 def run_pqs_case(case: dict, run_round: Callable, check_expected: bool = True, on_round: Optional[Callable] = None) -> None:
     env = Env()
-    tc = env.ev(case)
+    tc = MANUAL_PQS[case["manual"]](env.fx) if "manual" in case else env.ev(case)
     cfg: SchedulingConfig = tc["SchedulingConfig"]
     nodes: List[NodeSpec] = tc["Nodes"]
     rounds = tc["Rounds"]
