@@ -107,7 +107,10 @@ class Env:
             "pointer.MustParseResource": lambda s: s,
             "testfixtures.SingleQueuePriorityOne": lambda name: [{"Name": name, "PriorityFactor": 1.0}],
             "testfixtures.WithProtectedFractionOfFairShareConfig": lambda v, c: self._cfg(c, protected_fraction_of_fair_share=float(v)),
-            "testfixtures.WithRoundLimitsConfig": lambda l, c: self._cfg(c, maximum_resource_fraction_to_schedule=dict(l)),
+            "testfixtures.WithRoundLimitsConfig": lambda l, c: self._round_limits(c, dict(l)),
+            # MaximumResourceFractionToScheduleByPool: the pool's own map REPLACES the global one (constraints.go:208-214);
+            # the drivers schedule the pool "pool" (gang_scheduler_test.go:626,651)
+            "testfixtures.WithRoundLimitsPoolConfig": lambda by_pool, c: self._round_limits_pool(c, by_pool),
             "testfixtures.WithPerPriorityLimitsConfig": self._per_priority_limits,
             "testfixtures.WithGlobalSchedulingRateLimiterConfig": lambda r, b, c: self._cfg(c, maximum_scheduling_rate=float(r), maximum_scheduling_burst=int(b)),
             "testfixtures.WithPerQueueSchedulingLimiterConfig": lambda r, b, c: self._cfg(c, maximum_per_queue_scheduling_rate=float(r), maximum_per_queue_scheduling_burst=int(b)),
@@ -119,6 +122,18 @@ class Env:
         }
 
     # ---- helpers backing Go fixture functions ----------------------------------------------
+    def _round_limits(self, c, limits):
+        pool = getattr(c, "_pool_round_limits", None)
+        c2 = self._cfg(c, maximum_resource_fraction_to_schedule=dict(pool) if pool is not None else limits)
+        c2._pool_round_limits = pool
+        return c2
+
+    def _round_limits_pool(self, c, by_pool):
+        pool = by_pool.get("pool")
+        c2 = self._cfg(c, maximum_resource_fraction_to_schedule=dict(pool)) if pool is not None else self._cfg(c)
+        c2._pool_round_limits = dict(pool) if pool is not None else None
+        return c2
+
     @staticmethod
     def _cfg(c: SchedulingConfig, **kw) -> SchedulingConfig:
         for k, v in kw.items():
