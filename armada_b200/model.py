@@ -803,3 +803,65 @@ class RoundResult:
             if getattr(self.out, name) != getattr(other.out, name):
                 bad.append(f"{name}: {getattr(self.out, name)} vs {getattr(other.out, name)}")
         return bad
+
+
+def node_preemptibility_stats(b: "RoundInputBuilder", res: "RoundResult") -> List[Tuple[str, bool, str]]:
+    """EvictorResult.NodePreemptiblityStats of the round's first evictor (NewNodeEvictor with the fair-share filter,
+    preempting_queue_scheduler.go:93-136; eviction.go:197-273): per node, in node-id order, (node id, can every job on
+    it be preempted, the sorted reasons).  A report for operators (scheduling reports, cycle metrics), derived on the
+    host from the round's inputs and the fair shares the device computed — the evictions themselves happen on the
+    device (`k_evict_balance`) and `evictable_jobs` below is checked against them in the tests."""
+    reasons, _ = _eviction_reasons(b, res)
+    inp = b.input
+    by_node: Dict[int, List[int]] = {}
+    for j, n in enumerate(b.job_node[: len(b.jobs)]):
+        if n != abi.NONE:
+            by_node.setdefault(int(n), []).append(j)
+    out = []
+    for i in sorted(range(len(b.nodes)), key=lambda i: b.nodes[i].id):
+        node = b.nodes[i]
+        jobs = by_node.get(i, [])
+        if not jobs:  # nodeFilter: "node_empty" (eviction.go:88-95, 200-210)
+            rs = {"node_empty"} | ({"node_unschedulable"} if node.unschedulable else set())
+            out.append((node.id, not node.unschedulable, ",".join(sorted(rs))))
+            continue
+        rs = {reasons[j] for j in jobs if reasons[j]}
+        if node.unschedulable:
+            rs.add("node_unschedulable")
+        out.append((node.id, not rs, ",".join(sorted(rs)) if rs else "all_jobs_preemptible"))
+    return out
+
+
+def evictable_jobs(b: "RoundInputBuilder", res: "RoundResult") -> np.ndarray:
+    """The running jobs the first evictor's job filter lets through (bool[J])."""
+    return _eviction_reasons(b, res)[1]
+
+
+def _eviction_reasons(b: "RoundInputBuilder", res: "RoundResult"):
+    cfg, inp = b.cfg, b.input
+    J, D = len(b.jobs), b.factory.D
+    total = b.total_resources.astype(np.float64)
+    mult = np.array([inp.drf_multipliers[d] for d in range(D)])
+    # qctx.GetAllocation() = Allocated + ShortJobPenalty at the start of the round
+    alloc = b.qa.sum(axis=1).astype(np.float64) + b.qp.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        frac_d = np.where(total != 0, alloc / np.where(total != 0, total, 1.0), 0.0) * mult
+        actual = np.maximum(frac_d.max(axis=1), 0.0) if D else np.zeros(len(b.queues))
+        fs = res.queue_fair_share
+        fair = fs[:, 2] if cfg.protect_uncapped_adjusted_fair_share else np.maximum(fs[:, 1], fs[:, 0])
+        fraction = actual / fair[: len(actual)]
+    reasons: List[str] = [""] * J
+    evict = np.zeros(J, dtype=bool)
+    for j, spec in enumerate(b.jobs):
+        if b.job_node[j] == abi.NONE:
+            continue
+        q = b.job_queue[j]
+        if q == abi.NONE:
+            reasons[j] = "invalid_queue"
+        elif not cfg.priority_classes[spec.priority_class].preemptible:
+            reasons[j] = "job_not_preemptible"
+        elif fraction[q] <= cfg.protected_fraction_of_fair_share:  # (NaN compares false: evicted, like the reference)
+            reasons[j] = "below_protected_fair_share"
+        else:
+            evict[j] = True
+    return reasons, evict

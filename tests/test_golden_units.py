@@ -297,3 +297,34 @@ def test_per_queue_limits(name, pc_fraction, queue_fraction, want):
         assert (got == 2**63 - 1).all()
     else:
         assert list(got) == list(f.from_node({"cpu": want[0], "memory": want[1]}))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_node_preemptibility_stats_agree_with_the_round(seed):
+    """NodePreemptiblityStats (eviction.go:38-49,197-273) derived on the host: the job filter it restates selects exactly
+    the jobs the round evicted (running jobs that end RESCHEDULED or PREEMPTED when no oversubscribed eviction followed),
+    and the per-node summary follows the reference's rules."""
+    from armada_b200.model import evictable_jobs, node_preemptibility_stats
+    import gang_cases
+    b = gang_cases.uniformity_round(seed, floating=False, n_jobs=200)
+    res = oracle_lib.round_schedule(b.input)
+    ev = evictable_jobs(b, res)
+    running = b.job_node[: len(b.jobs)] != abi.NONE
+    if int(res.stats.evicted_pass2) == 0:
+        touched = np.isin(res.job_state[: len(b.jobs)], (abi.JOB_RESCHEDULED, abi.JOB_PREEMPTED)) & running
+        assert (touched == ev).all()
+    assert int(ev.sum()) == int(res.stats.evicted_pass1)
+    stats = node_preemptibility_stats(b, res)
+    assert [s[0] for s in stats] == sorted(n.id for n in b.nodes)
+    by_node = {}
+    for j, n in enumerate(b.job_node[: len(b.jobs)]):
+        if n != abi.NONE:
+            by_node.setdefault(b.nodes[int(n)].id, []).append(j)
+    for nid, preemptible, reason in stats:
+        jobs = by_node.get(nid, [])
+        if not jobs:
+            assert reason == "node_empty" and preemptible
+        elif preemptible:
+            assert reason == "all_jobs_preemptible" and all(ev[j] for j in jobs)
+        else:
+            assert not all(ev[j] for j in jobs) and set(reason.split(",")) <= {"job_not_preemptible", "below_protected_fair_share", "invalid_queue"}
