@@ -11,7 +11,7 @@ import pytest
 import fixtures as fx
 import go_tables as gt
 from armada_b200 import abi
-from armada_b200.model import FloatingResource, JobSpec, NodeSpec, QueueSpec, RoundInputBuilder
+from armada_b200.model import FloatingResource, QueueSpec, RoundInputBuilder
 
 GANG = gt.load_cases("gang_scheduler")
 
@@ -149,9 +149,7 @@ def uniformity_round(seed: int, n_nodes: int = 40, n_zones: int = 5, n_queues: i
     for i in range(n_nodes):
         labels = {} if rnd.random() < 0.1 else {"zone": f"z{rnd.randrange(n_zones)}"}
         nodes.append(F.node({"cpu": "32", "memory": "256Gi"}, labels=labels))
-    mem = "3Gi" if unaligned else "4Gi"  # 3Gi is not a multiple of the 128Mi... it is; use an odd Mi count for exact mode
-    if unaligned:
-        mem = "4100Mi"
+    mem = "4100Mi" if unaligned else "4Gi"  # 4100Mi is not a multiple of the 128Mi index resolution: exact mode
     jobs = []
     # running jobs of queue "a" (preemptible priorities 0..2) fill most nodes
     for n in nodes:

@@ -1,5 +1,10 @@
-import sys, os, time
-sys.path.insert(0, "/root/repo")
+"""Upload / run / download wall-clock of ONE pool through the C ABI with host buffers, with the upload's phase laps
+(ARMADA_TIME_UPLOAD=1).  Dev tooling; needs a GPU."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from armada_b200 import synth
 from armada_b200.scheduler import DeviceRound
 r = synth.config_c3()
