@@ -154,6 +154,8 @@ class RoundOutput(C.Structure):
         ("scheduled_resources", i64p),
         ("evicted_resources", i64p),
         ("job_excluded_nodes", u32p),
+        ("job_seq_first_pass", u32p),
+        ("job_reason_first_pass", u8p),
         ("num_scheduled_jobs", C.c_uint32),
         ("num_scheduled_gangs", C.c_uint32),
         ("num_evicted_jobs", C.c_int32),

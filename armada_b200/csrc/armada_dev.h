@@ -137,6 +137,9 @@ struct DevPtrs {
   int32_t* res_preempted_at;       // [J]
   uint8_t* res_method;             // [J]
   uint32_t* res_seq;               // [J] loop iteration of the job's last gang attempt
+  // the first schedule pass as it ended (copies taken between the passes: the inputs of QueueStats)
+  uint32_t* fp_seq;                // [J] res_seq
+  uint8_t* fp_flags;               // [4][J] q_successful, q_rescheduled, q_unsuccessful, q_reason
   uint32_t* gang_fill;             // [G] members gathered so far by the gang iterator
   uint32_t* gang_buf;              // [sum gang_count] members in arrival order
   int32_t* ev_index_of_job;        // [J] "evictedJobs" table: index or -1

@@ -744,7 +744,11 @@ class RoundInputBuilder:
 class RoundResult:
     """Caller-allocated ArmadaRoundOutput + numpy views."""
 
-    def __init__(self, inp: abi.RoundInput):
+    # ask for job_seq_first_pass / job_reason_first_pass (the inputs of `queue_stats`); off by default: 5 bytes per job
+    # more to bring back per round.  tests/conftest.py switches it on for every test.
+    FIRST_PASS_DEFAULT = False
+
+    def __init__(self, inp: abi.RoundInput, first_pass: Optional[bool] = None):
         J, N, Q = max(inp.num_jobs, 1), max(inp.num_nodes, 1), max(inp.num_queues, 1)
         D, PL, PC = inp.num_resources, inp.num_priorities, inp.num_priority_classes
         self.job_state = np.zeros(J, np.uint8)
@@ -761,6 +765,8 @@ class RoundResult:
         self.scheduled_resources = np.zeros(D, np.int64)
         self.evicted_resources = np.zeros(D, np.int64)
         self.job_excluded_nodes = np.zeros((J, abi.EXCLUDED_KINDS), np.uint32)
+        self.job_seq_first_pass = np.zeros(J, np.uint32)
+        self.job_reason_first_pass = np.zeros(J, np.uint8)
         o = abi.RoundOutput()
         o.job_state = self.job_state.ctypes.data_as(abi.u8p)
         o.job_node = self.job_node.ctypes.data_as(abi.u32p)
@@ -777,6 +783,10 @@ class RoundResult:
         o.evicted_resources = self.evicted_resources.ctypes.data_as(abi.i64p)
         if inp.collect_excluded_nodes:
             o.job_excluded_nodes = self.job_excluded_nodes.ctypes.data_as(abi.u32p)
+        self.first_pass = RoundResult.FIRST_PASS_DEFAULT if first_pass is None else first_pass
+        if self.first_pass:
+            o.job_seq_first_pass = self.job_seq_first_pass.ctypes.data_as(abi.u32p)
+            o.job_reason_first_pass = self.job_reason_first_pass.ctypes.data_as(abi.u8p)
         self.out = o
         self.stats = abi.RoundStats()
         self.num_jobs = inp.num_jobs
@@ -790,7 +800,8 @@ class RoundResult:
     def diff(self, other: "RoundResult") -> List[str]:
         """Bit-exact comparison of every output; returns a list of human-readable mismatches."""
         bad = []
-        for name in self.ARRAYS:
+        names = self.ARRAYS + (("job_seq_first_pass", "job_reason_first_pass") if self.first_pass and other.first_pass else ())
+        for name in names:
             x, y = getattr(self, name), getattr(other, name)
             if x.dtype.kind == "f":
                 eq = x.view(np.uint64) == y.view(np.uint64)
@@ -865,3 +876,97 @@ def _eviction_reasons(b: "RoundInputBuilder", res: "RoundResult"):
         else:
             evict[j] = True
     return reasons, evict
+
+
+# constraints.go:17-55 + gang_scheduler.go:168-216: the strings behind ARMADA_REASON_*
+REASON_TEXT = {
+    abi.REASON_MAX_RESOURCES_SCHEDULED: "maximum resources scheduled",
+    abi.REASON_MAX_RESOURCES_PER_QUEUE: "resource limit exceeded",
+    abi.REASON_GLOBAL_RATE_LIMIT: "global scheduling rate limit exceeded",
+    abi.REASON_QUEUE_RATE_LIMIT: "queue scheduling rate limit exceeded",
+    abi.REASON_QUEUE_CORDONED: "queue cordoned",
+    abi.REASON_GLOBAL_RATE_LIMIT_GANG: "gang would exceed global scheduling rate limit",
+    abi.REASON_QUEUE_RATE_LIMIT_GANG: "gang would exceed queue scheduling rate limit",
+    abi.REASON_GANG_EXCEEDS_GLOBAL_BURST: "gang cardinality too large: exceeds global max burst size",
+    abi.REASON_GANG_EXCEEDS_QUEUE_BURST: "gang cardinality too large: exceeds queue max burst size",
+    abi.REASON_GANG_DOES_NOT_FIT: "unable to schedule gang since minimum cardinality not met",
+    abi.REASON_JOB_DOES_NOT_FIT: "job does not fit on any node",
+    abi.REASON_UNIFORMITY_LABEL_NOT_INDEXED: "uniformity label is not indexed",
+    abi.REASON_NO_NODES_WITH_UNIFORMITY_LABEL: "no nodes with uniformity label",
+    abi.REASON_GANG_FITS_NO_UNIFORMITY_VALUE: "at least one job in the gang does not fit on any node",
+    abi.REASON_FLOATING_RESOURCES: "floating resource limit",
+}
+
+
+@dataclass
+class QueueStats:
+    """scheduling.QueueStats (result.go:15-28) without the wall-clock `Time`."""
+    gangs_considered: int = 0
+    jobs_considered: int = 0
+    gangs_scheduled: int = 0
+    first_gang_considered_sample_job_id: str = ""
+    first_gang_considered_result: str = ""
+    first_gang_considered_queue_position: int = 0
+    last_gang_scheduled_sample_job_id: str = ""
+    last_gang_scheduled_queue_position: int = 0
+    last_gang_scheduled_queue_cost: float = 0.0
+    last_gang_scheduled_resources: Optional[np.ndarray] = None
+    last_gang_scheduled_queue_resources: Optional[np.ndarray] = None
+
+
+def queue_stats(b: "RoundInputBuilder", res: "RoundResult") -> Dict[str, QueueStats]:
+    """SchedulingResult.AdditionalSchedulingInfo.StatsPerQueue: the statistics QueueScheduler.Schedule keeps per queue
+    (queue_scheduler.go:190-235) for the FIRST schedule pass of the round (preempting_queue_scheduler.go:270-272), from
+    the device's first-pass view (`job_seq_first_pass`, `job_reason_first_pass`).  A gang = the jobs of one loop
+    iteration; its sample job = gctx.JobIds()[0], the first member in queue order; loopNumber = iteration − 1.  The
+    queue's allocation and cost at its last scheduled gang are REPLAYED from the start-of-pass allocation (the
+    snapshot's minus what the first evictor took) plus the first-pass successes up to that iteration."""
+    if not res.first_pass:
+        raise ValueError("queue_stats needs a RoundResult created with first_pass=True")
+    J, f, cfg = len(b.jobs), b.factory, b.cfg
+    seq, why = res.job_seq_first_pass[:J], res.job_reason_first_pass[:J]
+    req = b.class_request[b.job_class[:J]] if J else np.zeros((0, f.D), np.int64)
+    pcprio = np.array([cfg.priority_classes[j.priority_class].priority for j in b.jobs], np.int64)
+    running = b.job_node[:J] != abi.NONE
+
+    def order_key(j):  # SchedulingOrderCompare (jobdb/comparison.go:49-107)
+        return (0 if running[j] else 1, -pcprio[j], b.job_qp[j], b.job_art[j] if running[j] else 0, b.job_st[j], b.job_id_rank[j])
+
+    evicted = evictable_jobs(b, res)
+    total = b.total_resources.astype(np.float64)
+    mult = np.array([b.input.drf_multipliers[d] for d in range(f.D)])
+    out: Dict[str, QueueStats] = {}
+    for qi, q in enumerate(b.queues):
+        mine = np.nonzero((b.job_queue[:J] == qi) & (seq > 0))[0]
+        if len(mine) == 0:
+            continue
+        st = QueueStats()
+        gangs: Dict[int, List[int]] = {}
+        for j in mine:
+            gangs.setdefault(int(seq[j]), []).append(int(j))
+        alloc = b.qa[qi].sum(axis=0) + b.qp[qi]  # qctx.GetAllocation(): Allocated + ShortJobPenalty
+        for j in np.nonzero((b.job_queue[:J] == qi) & evicted)[0]:
+            alloc = alloc - req[j]
+        for s in sorted(gangs):
+            members = sorted(gangs[s], key=order_key)
+            ok = all(why[j] == 0 for j in members)
+            st.gangs_considered += 1
+            st.jobs_considered += len(members)
+            if st.first_gang_considered_sample_job_id == "":
+                st.first_gang_considered_sample_job_id = b.jobs[members[0]].id
+                st.first_gang_considered_queue_position = s - 1
+                st.first_gang_considered_result = "scheduled" if ok else REASON_TEXT.get(int(why[members[0]]), str(int(why[members[0]])))
+            if ok:
+                st.gangs_scheduled += 1
+                gang_total = req[members].sum(axis=0)
+                alloc = alloc + gang_total
+                st.last_gang_scheduled_sample_job_id = b.jobs[members[0]].id
+                st.last_gang_scheduled_queue_position = s - 1
+                st.last_gang_scheduled_resources = gang_total
+                st.last_gang_scheduled_queue_resources = alloc.copy()
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    frac = np.where(total != 0, alloc / np.where(total != 0, total, 1.0), 0.0) * mult
+                cost = max(float(frac.max()), 0.0) if f.D else 0.0
+                st.last_gang_scheduled_queue_cost = cost / float(b.qw[qi])
+        out[q.name] = st
+    return out

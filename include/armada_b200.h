@@ -281,6 +281,12 @@ typedef struct {
    * disallowedResourceRequested.  The kinds of an attempted job sum to num_nodes
    * (queue_scheduler_test.go:656-676); all zero for every other job.  Needs collect_excluded_nodes.  */
   uint32_t* job_excluded_nodes;  /* [J][ARMADA_EXCLUDED_KINDS], or NULL                          */
+  /* The FIRST schedule pass as the QueueScheduler loop saw it — what QueueStats are made of
+     (queue_scheduler.go:190-235; the round reports the first pass's, preempting_queue_scheduler.go:270-272):
+     job_seq / job_reason above describe a job's LAST attempt over both passes.  Either may be NULL. */
+  uint32_t* job_seq_first_pass;    /* [J] 1-based loop iteration of the job's attempt in the first pass, 0 = none   */
+  uint8_t* job_reason_first_pass;  /* [J] ARMADA_REASON_* of that attempt when it failed (incl. the round-terminating
+                                      reasons, which leave no job-level record), 0 = it succeeded / no attempt       */
   uint32_t num_scheduled_jobs;   /* sctx.NumScheduledJobs                                     */
   uint32_t num_scheduled_gangs;  /* sctx.NumScheduledGangs                                    */
   int32_t num_evicted_jobs;      /* sctx.NumEvictedJobs                                       */

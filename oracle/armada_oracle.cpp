@@ -872,6 +872,10 @@ struct Round {
   // latest pod scheduling result per job (the jctx the result lists would carry)
   std::vector<JobCtx> last_jctx;
   std::vector<uint32_t> job_seq;  // loop iteration of the job's last gang attempt
+  // the first schedule pass as the loop saw it (what QueueStats are made of, queue_scheduler.go:190-235)
+  bool in_first_pass = false;
+  std::vector<uint32_t> job_seq_first;
+  std::vector<uint8_t> job_reason_first;
   std::vector<std::vector<uint32_t>> queued_by_queue;
   ArmadaRoundStats stats{};
   std::vector<std::vector<uint32_t>> gang_members;  // jobRepo.GetGangJobsByGangId
@@ -892,6 +896,8 @@ struct Round {
     unfeasible_key.assign(C, 0);
     last_jctx.resize(J);
     job_seq.assign(J, 0);
+    job_seq_first.assign(J, 0);
+    job_reason_first.assign(J, 0);
     global_tokens = in->global_limiter_tokens;
     gang_members.resize(in->num_gangs);
     for (uint32_t j = 0; j < J; ++j)
@@ -1547,6 +1553,11 @@ struct Round {
       for (JobCtx* jc : g.jctxs) job_seq[jc->job] = (uint32_t)stats.loop_iterations;
       uint8_t reason = ARMADA_REASON_NONE;
       bool ok = gang_schedule(g, skip_key_check, &reason);
+      if (in_first_pass)
+        for (JobCtx* jc : g.jctxs) {
+          job_seq_first[jc->job] = (uint32_t)stats.loop_iterations;
+          job_reason_first[jc->job] = ok ? (uint8_t)ARMADA_REASON_NONE : reason;
+        }
       candidate_clear(ci);
       if (ok) {
         for (JobCtx* jc : g.jctxs)
@@ -1708,7 +1719,9 @@ struct Round {
 
     // 2. re-schedule evicted + schedule new (:140-164)
     uint32_t term1 = 0;
+    in_first_pass = true;
     std::vector<uint32_t> res1 = schedule_pass(repo, true, false, false, &term1);
+    in_first_pass = false;
     termination_reason = term1;
     for (uint32_t j : res1) {
       if (preempted[j]) preempted[j] = 0;
@@ -1807,6 +1820,8 @@ struct Round {
       if (out->job_method) out->job_method[j] = has ? jc.p_method : (uint8_t)ARMADA_METHOD_NONE;
       if (out->job_reason) out->job_reason[j] = unsuccessful[j] ? unsuccessful_reason[j] : (uint8_t)ARMADA_REASON_NONE;
       if (out->job_seq) out->job_seq[j] = job_seq[j];
+      if (out->job_seq_first_pass) out->job_seq_first_pass[j] = job_seq_first[j];
+      if (out->job_reason_first_pass) out->job_reason_first_pass[j] = job_reason_first[j];
       if (out->job_excluded_nodes && in->collect_excluded_nodes) {
         const bool single_failed = st == ARMADA_JOB_FAILED && jc.job != NONE && jc.has_pctx && in->job_gang[j] == NONE;
         for (uint32_t k = 0; k < ARMADA_EXCLUDED_KINDS; ++k) out->job_excluded_nodes[(size_t)j * ARMADA_EXCLUDED_KINDS + k] = single_failed ? jc.excl[k] : 0u;

@@ -328,3 +328,40 @@ def test_node_preemptibility_stats_agree_with_the_round(seed):
             assert reason == "all_jobs_preemptible" and all(ev[j] for j in jobs)
         else:
             assert not all(ev[j] for j in jobs) and set(reason.split(",")) <= {"job_not_preemptible", "below_protected_fair_share", "invalid_queue"}
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_queue_stats_from_the_first_pass_view(seed):
+    """QueueStats (queue_scheduler.go:190-235, result.go:15-28) derived from job_seq_first_pass / job_reason_first_pass:
+    counts and positions are consistent with the round's outcome, and the replayed queue allocation at a queue's last
+    scheduled gang ends where the round's own accounting ends when nothing happened after the first pass."""
+    from armada_b200.model import queue_stats
+    import gang_cases
+    b = gang_cases.uniformity_round(seed, floating=False, n_jobs=220)
+    res = oracle_lib.round_schedule(b.input)
+    stats = queue_stats(b, res)
+    J = len(b.jobs)
+    seq = res.job_seq_first_pass[:J]
+    assert seq.max() <= int(res.stats.loop_iterations) and (seq > 0).sum() > 0
+    positions = set()
+    for qi, q in enumerate(b.queues):
+        mine = (b.job_queue[:J] == qi) & (seq > 0)
+        if not mine.any():
+            assert q.name not in stats
+            continue
+        st = stats[q.name]
+        assert st.jobs_considered == int(mine.sum()) and st.gangs_considered == len(set(seq[mine].tolist()))
+        assert st.gangs_scheduled <= st.gangs_considered
+        assert st.first_gang_considered_queue_position == int(seq[mine].min()) - 1
+        assert st.first_gang_considered_result == "scheduled" or st.first_gang_considered_result in gt_reason_texts()
+        positions.add(st.first_gang_considered_queue_position)
+        if int(res.stats.evicted_pass2) == 0 and st.gangs_scheduled:
+            # nothing moved after the first pass: the replay's last allocation (incl. the short-job penalty, zero here)
+            # is the queue's final allocation
+            assert (st.last_gang_scheduled_queue_resources == res.queue_allocated[qi] + b.qp[qi]).all()
+    assert 0 in positions  # some queue was looked at in the very first iteration
+
+
+def gt_reason_texts():
+    from armada_b200.model import REASON_TEXT
+    return set(REASON_TEXT.values())
