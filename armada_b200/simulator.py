@@ -727,3 +727,36 @@ def simulate_files(cluster_path: str, workload_path: str, config_path: str, outp
     sink = ParquetSink(output_dir) if output_dir else MemorySink()
     sim = Simulator(cluster_spec_from_file(cluster_path), workload_spec_from_file(workload_path), cfg, default_pc, engine=engine, sink=sink, **kw)
     return sim.run()
+
+
+def main(argv: Optional[Sequence[str]] = None) -> int:
+    """cmd/simulator's command line (cmd/simulator/cmd/root.go:24-33): `python -m armada_b200.simulator --clusters C.yaml
+    --workloads W.yaml --config S.yaml --outputDir out/`.  Every round runs on cuda:0 (no CPU path)."""
+    import argparse
+    import os
+    import sys
+    import time
+    ap = argparse.ArgumentParser(prog="armada_b200.simulator")
+    ap.add_argument("--clusters", required=True, help="Path specifying cluster configurations to simulate.")
+    ap.add_argument("--workloads", required=True, help="Path specifying workloads to simulate.")
+    ap.add_argument("--config", required=True, help="Path to scheduler configurations to simulate.")
+    ap.add_argument("--outputDir", default="", help="Directory for jobs.parquet / queue_stats.parquet (default: a timestamped directory).")
+    ap.add_argument("--overwriteOutputDir", action="store_true")
+    ap.add_argument("--enableFastForward", action="store_true", help="Skips schedule events when we're in a steady state")
+    ap.add_argument("--hardTerminationMinutes", type=int, default=-1, help="Limit the time simulated.  -1 for no limit.")
+    ap.add_argument("--schedulerCyclePeriodSeconds", type=int, default=10)
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args(argv)
+    out = a.outputDir or time.strftime("armada_simulator_%Y_%m_%d_%H_%M_%S")
+    if os.path.exists(out) and os.listdir(out) and not a.overwriteOutputDir:
+        print(f"output directory {out} already exists and is not empty (use --overwriteOutputDir)", file=sys.stderr)
+        return 1
+    t0 = time.perf_counter()
+    s = simulate_files(a.clusters, a.workloads, a.config, output_dir=out, engine=device_engine(a.device), enable_fast_forward=a.enableFastForward,
+                       hard_termination_minutes=max(a.hardTerminationMinutes, 0), scheduler_cycle_period_seconds=a.schedulerCyclePeriodSeconds)
+    print(f"simulated {s.time / NS:.0f} s in {s.rounds} rounds, {len(s.sink.job_rows)} job rows -> {out} ({time.perf_counter() - t0:.1f} s wall)")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -158,3 +158,31 @@ def test_c1_on_the_device_matches_the_oracle_driven_run():
     assert dev.sink.job_rows == ref.sink.job_rows
     assert repr(dev.sink.queue_rows) == repr(ref.sink.queue_rows)  # (gpu_share is NaN = 0/0 like the reference's: compare the text)
     assert dev.transitions == ref.transitions
+
+
+def test_command_line(tmp_path, monkeypatch, capsys):
+    """cmd/simulator's flags (cmd/simulator/cmd/root.go:24-33); the product engine is the device — here swapped for the
+    oracle so that the host logic runs on a CPU box."""
+    monkeypatch.setattr(sim, "device_engine", lambda device=0: oracle_engine)
+    out = str(tmp_path / "o")
+    args = ["--clusters", os.path.join(SIMDIR, "cluster_100x32.yaml"), "--workloads", os.path.join(SIMDIR, "workload_1k.yaml"),
+            "--config", os.path.join(SIMDIR, "config_basic.yaml"), "--outputDir", out, "--hardTerminationMinutes", "2"]
+    assert sim.main(args) == 0
+    assert "job rows" in capsys.readouterr().out
+    assert sorted(os.listdir(out)) == ["jobs.parquet", "queue_stats.parquet"]
+    assert sim.main(args) == 1  # exists and is not empty
+    assert sim.main(args + ["--overwriteOutputDir"]) == 0
+
+
+def test_the_product_engine_needs_the_device():
+    import ctypes
+    from armada_b200 import abi
+    try:
+        ctypes.CDLL("libcuda.so.1")
+        have_driver = True
+    except OSError:
+        have_driver = False
+    if have_driver:
+        pytest.skip("a CUDA driver is present")
+    with pytest.raises((abi.ArmadaError, OSError)):
+        sim.device_engine(0)
