@@ -74,6 +74,13 @@ SCENARIOS = {
                    lambda: workload(("A", [jt32(2, "foo", fx.PriorityClass0)]), ("B", [jt32(1, "bar", fx.PriorityClass0, earliest_submit_time=30 * sim.NS)])), 5,
                    [("submit", "A", 2), ("leased", "A", 2), ("submit", "B", 1), ("preempted", "A", 1), ("leased", "B", 1), ("submit", "A", 1),
                     ("succeeded", "A", 1), ("leased", "A", 1), ("succeeded", "B", 1), ("succeeded", "A", 1)]),
+    # :233-290: A's job preempts one of C's; the preempted job comes back without pushing anything else out
+    "No preemption cascade": (cluster(("TestCluster1", 1), ("TestCluster2", 1), ("TestCluster3", 1)),
+                              lambda: workload(("B", [jt32(1, "foo", fx.PriorityClass0)]), ("C", [jt32(2, "foo", fx.PriorityClass0)]),
+                                               ("A", [jt32(1, "foo", fx.PriorityClass0, earliest_submit_time=30 * sim.NS)])), 5,
+                              [("submit", "B", 1), ("submit", "C", 2), ("leased", "B", 1), ("leased", "C", 2), ("submit", "A", 1), ("preempted", "C", 1),
+                               ("leased", "A", 1), ("submit", "C", 1), ("succeeded", "B", 1), ("succeeded", "C", 1), ("leased", "C", 1), ("succeeded", "A", 1),
+                               ("succeeded", "C", 1)]),
     # :441-479: Cluster2 is too small for a gang; the uniformity label (the cluster name) keeps every gang on Cluster1
     "Gang Job": (cluster(("Cluster1", 8), ("Cluster2", 1)), lambda: workload(("A", [jt32(16, "foo", DEFAULT, gang_cardinality=8)])), 5,
                  [("submit", "A", 16), ("leased", "A", 8), ("succeeded", "A", 8), ("leased", "A", 8), ("succeeded", "A", 8)]),
@@ -186,3 +193,38 @@ def test_the_product_engine_needs_the_device():
         pytest.skip("a CUDA driver is present")
     with pytest.raises((abi.ArmadaError, OSError)):
         sim.device_engine(0)
+
+
+def _home_away_scenario():
+    """"Home-away preemption" (simulator_test.go:332-440): 32 one-GPU away jobs fill both clusters (16 of them away on the
+    tainted whale nodes); two whole-node home jobs arrive, push the 16 away jobs out, run, and the 16 come back."""
+    from armada_b200.model import AwayNodeType, PriorityClass, Taint, Toleration
+    whale = Taint("gpu-whale", "true", "NoSchedule")
+    gpu_node = {"cpu": "128", "memory": "4096Gi", "nvidia.com/gpu": "8"}  # NodeTemplateGpu, test_utils.go:106-116
+    cl = sim.ClusterSpec("cluster", [sim.Cluster("WhaleCluster", "TestPool", [sim.NodeTemplate(2, gpu_node, {}, (whale,))]),
+                                     sim.Cluster("TestCluster", "TestPool", [sim.NodeTemplate(2, gpu_node)])])
+    wl = sim.WorkloadSpec("w", [
+        sim.Queue("queue-0", 1.0, [sim.JobTemplate(id="queue-0-template-0", queue="queue-0", number=2, job_set="job-set-0", priority_class_name="armada-preemptible",
+                                                   requests=dict(gpu_node), tolerations=(Toleration("gpu-whale", "", "true", "NoSchedule"),),
+                                                   earliest_submit_time=MIN, runtime=sim.ShiftedExponential(minimum=5 * MIN))]),
+        sim.Queue("queue-1", 1.0, [sim.JobTemplate(id="queue-1-template-0", queue="queue-1", number=32, job_set="job-set-1", priority_class_name="armada-preemptible-away",
+                                                   requests={"cpu": "16", "memory": "512Gi", "nvidia.com/gpu": "1"}, runtime=sim.ShiftedExponential(minimum=60 * MIN))])], random_seed=1)
+    cfg = fx.test_scheduling_config(priority_classes={"armada-preemptible-away": PriorityClass(30000, True, (AwayNodeType(29000, "gpu-whale"),)),
+                                                      "armada-preemptible": PriorityClass(30000, True)},
+                                    well_known_node_types={"gpu-whale": (whale,)})
+    want = [("submit", "queue-1", 32), ("leased", "queue-1", 32), ("submit", "queue-0", 2), ("preempted", "queue-1", 16), ("leased", "queue-0", 2),
+            ("submit", "queue-1", 16), ("succeeded", "queue-0", 2), ("leased", "queue-1", 16), ("succeeded", "queue-1", 32)]
+    return cl, wl, cfg, want
+
+
+def test_home_away_preemption_scenario():
+    cl, wl, cfg, want = _home_away_scenario()
+    s = sim.Simulator(cl, wl, cfg, engine=oracle_engine, hard_termination_minutes=24 * 60).run()
+    assert summary(s) == want
+
+
+@pytest.mark.gpu
+def test_home_away_preemption_scenario_on_the_device():
+    cl, wl, cfg, want = _home_away_scenario()
+    s = sim.Simulator(cl, wl, cfg, engine=sim.device_engine(0), hard_termination_minutes=24 * 60).run()
+    assert summary(s) == want
