@@ -467,3 +467,22 @@ def test_presorted_job_order_fast_path_equals_the_general_path(monkeypatch):
         general, _ = assert_parity(inp, f"{name} general order path")
         monkeypatch.delenv("ARMADA_NO_PRESORTED")
         assert not fast.diff(general)
+
+
+def test_job_order_over_several_host_slices():
+    """70 000 jobs: the upload ranks them on 16 host threads.  (1) queues that arrive in order: the one-pass ranking,
+    checked inside every slice and across the slices of a queue; (2) the same round with two jobs of one queue
+    exchanged ACROSS a slice boundary (only the cross-slice check can see it) and (3) inside a slice: the bucket sort."""
+    r = synth.scaled("C2", 0.7)
+    assert len(r.job_queue) >= 65536
+    assert_parity(r.to_input(), "presorted, 16 slices")
+    per_slice = len(r.job_queue) // 16
+    for name, lo, hi in (("across slices", per_slice - 40, per_slice + 40), ("inside a slice", 100, 180)):
+        r = synth.scaled("C2", 0.7)
+        q = r.job_queue[lo]
+        a = next(j for j in range(lo, hi) if r.job_queue[j] == q and j < per_slice) if name == "across slices" else lo
+        b = next(j for j in range(hi, lo, -1) if r.job_queue[j] == q and (j >= per_slice or name != "across slices"))
+        assert a < b and r.job_queue[a] == r.job_queue[b]
+        r.job_submit_time[a], r.job_submit_time[b] = r.job_submit_time[b], r.job_submit_time[a]
+        got, want = assert_parity(r.to_input(), name)
+        assert want.job_seq[b] < want.job_seq[a] or want.job_seq[a] == 0  # b now comes first in its queue
