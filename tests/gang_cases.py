@@ -133,7 +133,7 @@ def check_gang_case(b, tc, gangs, res):
 
 
 def uniformity_round(seed: int, n_nodes: int = 40, n_zones: int = 5, n_queues: int = 4, n_jobs: int = 260, floating: bool = True,
-                     unaligned: bool = False) -> RoundInputBuilder:
+                     unaligned: bool = False, max_gang: int = 6, running_gangs: int = 0, protected_fraction: float = 0.5) -> RoundInputBuilder:
     """Nodes spread over `n_zones` values of the label "zone" (a few nodes without it), partly filled with running
     preemptible jobs of an over-served queue (so attempts differ in what they preempt: the fit's mean
     PreemptedAtPriority), queued single jobs and gangs — some gangs with the uniformity label "zone", some with a label
@@ -142,7 +142,7 @@ def uniformity_round(seed: int, n_nodes: int = 40, n_zones: int = 5, n_queues: i
     rnd = random.Random(seed)
     F = fx.Fixtures()
     cfg = fx.test_scheduling_config(indexed_node_labels=list(fx.test_scheduling_config().indexed_node_labels) + ["zone", "rack"],
-                                    protected_fraction_of_fair_share=0.5)
+                                    protected_fraction_of_fair_share=protected_fraction)
     if floating:
         cfg.floating_resources = [FloatingResource("licences", "1", str(rnd.randint(6, 30)))]
     nodes = []
@@ -162,6 +162,21 @@ def uniformity_round(seed: int, n_nodes: int = 40, n_zones: int = 5, n_queues: i
             jobs.append(j)
     queues = ["a"] + [f"q{i}" for i in range(n_queues - 1)]
     gid = 0
+    # running gangs with a uniformity label (evicted and re-scheduled as gangs: every member is pinned to its node)
+    for g in range(running_gangs):
+        zone_nodes = [n for n in nodes if n.labels.get("zone") == f"z{g % n_zones}"]
+        if len(zone_nodes) < 2:
+            continue
+        pc = rnd.choice([fx.PriorityClass0, fx.PriorityClass1])
+        card = rnd.randint(2, 4)
+        gid += 1
+        for m in range(card):
+            j = F.job("a", pc, {"cpu": "2", "memory": "8Gi"})
+            j.node = zone_nodes[m % len(zone_nodes)].id
+            j.scheduled_at_priority = fx.test_priority_classes()[pc].priority
+            j.active_run_timestamp = len(jobs)
+            j.gang_id, j.gang_cardinality, j.gang_node_uniformity_label = f"rg{gid}", card, "zone"
+            jobs.append(j)
     while len(jobs) < n_jobs:
         q = rnd.choice(queues[1:])
         pc = rnd.choice([fx.PriorityClass0, fx.PriorityClass1, fx.PriorityClass2, fx.PriorityClass3])
@@ -172,7 +187,7 @@ def uniformity_round(seed: int, n_nodes: int = 40, n_zones: int = 5, n_queues: i
         if kind < 0.45:
             jobs.append(F.job(q, pc, req))
             continue
-        card = rnd.randint(2, 6)
+        card = rnd.randint(2, max_gang)
         gid += 1
         label = None
         r = rnd.random()
@@ -186,5 +201,18 @@ def uniformity_round(seed: int, n_nodes: int = 40, n_zones: int = 5, n_queues: i
         for m in members:
             m.gang_id, m.gang_cardinality, m.gang_node_uniformity_label = f"g{gid}", card, label
         jobs += members
-    qs = [QueueSpec(q, rnd.choice([1.0, 2.0])) for q in queues]
+    # the snapshot's queue accounting (calculateJobSchedulingInfo): allocation = the running jobs, demand = every job
+    import numpy as np
+    f = cfg.factory()
+    qs = []
+    for q in queues:
+        alloc, demand = {}, np.zeros(f.D, np.int64)
+        for j in jobs:
+            if j.queue != q:
+                continue
+            r = f.from_job(j.requests)
+            demand += r
+            if j.node is not None:
+                alloc[j.priority_class] = alloc.get(j.priority_class, np.zeros(f.D, np.int64)) + r
+        qs.append(QueueSpec(q, rnd.choice([1.0, 2.0]), False, alloc, demand.copy(), demand.copy()))
     return RoundInputBuilder(cfg, nodes, jobs, qs)

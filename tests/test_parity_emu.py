@@ -486,3 +486,14 @@ def test_job_order_over_several_host_slices():
         r.job_submit_time[a], r.job_submit_time[b] = r.job_submit_time[b], r.job_submit_time[a]
         got, want = assert_parity(r.to_input(), name)
         assert want.job_seq[b] < want.job_seq[a] or want.job_seq[a] == 0  # b now comes first in its queue
+
+
+@pytest.mark.parametrize("seed", [50, 51, 52, 53])
+def test_uniformity_rounds_with_large_and_running_gangs(seed):
+    """Gangs of up to 40 members (more than one warp load of members per attempt) and running gangs with a uniformity
+    label that are evicted and re-scheduled (pinned members inside the per-value attempts)."""
+    b = gang_cases.uniformity_round(seed, n_nodes=60, n_zones=4, n_jobs=500, floating=(seed % 2 == 0), max_gang=40, running_gangs=6,
+                                    protected_fraction=0.0 if seed >= 52 else 0.5)
+    got, want = assert_parity(b.input, f"large / running uniformity gangs {seed}")
+    if seed >= 52:
+        assert int(want.stats.evicted_pass1) > 0  # the running gangs are evicted and go through the search pinned
