@@ -1437,7 +1437,7 @@ struct Round {
     std::vector<uint8_t> only_yield_evicted_by_queue;
   };
   // QueueCandidateGangIteratorPQ.Less :628-674
-  bool pq_less(const CandidateIt& ci, const PQItem& a, const PQItem& b) const {
+  static bool pq_less(const CandidateIt& ci, const PQItem& a, const PQItem& b) {
     if (ci.consider_priority && a.pc_priority != b.pc_priority) return a.pc_priority > b.pc_priority;
     if (ci.prioritise_larger) {
       bool au = a.proposed <= a.budget, bu = b.proposed <= b.budget;
@@ -1932,6 +1932,18 @@ int32_t armada_oracle_round_schedule(const ArmadaRoundInput* in, ArmadaRoundOutp
     r.run(out);
     if (stats) *stats = r.stats;
   });
+}
+
+// QueueCandidateGangIteratorPQ.Less on two items given as {proposedQueueCost, currentQueueCost, queueBudget, itemSize,
+// queue rank, priority-class priority} (test hook: TestQueueCandidateGangIteratorPQ_* vectors)
+int32_t armada_oracle_pq_less(int32_t prioritise_larger, int32_t consider_priority, const double* a, const double* b) {
+  Round::CandidateIt ci;
+  ci.prioritise_larger = prioritise_larger != 0;
+  ci.consider_priority = consider_priority != 0;
+  Round::PQItem x{}, y{};
+  x.proposed = a[0], x.current = a[1], x.budget = a[2], x.item_size = a[3], x.queue = (uint32_t)a[4], x.pc_priority = (int32_t)a[5];
+  y.proposed = b[0], y.current = b[1], y.budget = b[2], y.item_size = b[3], y.queue = (uint32_t)b[4], y.pc_priority = (int32_t)b[5];
+  return Round::pq_less(ci, x, y) ? 1 : 0;
 }
 
 double armada_oracle_drf_cost(uint32_t d, const int64_t* total, const double* multipliers, const int64_t* allocation) {

@@ -28,6 +28,8 @@ int32_t armada_oracle_round_schedule(const ArmadaRoundInput* in, ArmadaRoundOutp
 const char* armada_oracle_last_error(void);
 
 /* DominantResourceFairness.UnweightedCostFromAllocation (fairness/fairness.go:103-105). */
+/* QueueCandidateGangIteratorPQ.Less (queue_scheduler.go:628-674) on {proposed, current, budget, itemSize, queue rank, pc priority} */
+int32_t armada_oracle_pq_less(int32_t prioritise_larger, int32_t consider_priority, const double* a, const double* b);
 double armada_oracle_drf_cost(uint32_t d, const int64_t* total, const double* multipliers,
                               const int64_t* allocation);
 

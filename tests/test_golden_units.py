@@ -365,3 +365,36 @@ def test_queue_stats_from_the_first_pass_view(seed):
 def gt_reason_texts():
     from armada_b200.model import REASON_TEXT
     return set(REASON_TEXT.values())
+
+
+PQ_ORDER = {
+    # queue_scheduler_test.go:699-834 — items {queue: (proposedQueueCost, currentQueueCost, queueBudget, itemSize)}, expected sort.Sort order
+    "BelowFairShare_EvenCurrentCost": ({"A": (2, 0, 5, 2), "B": (3, 0, 5, 3), "C": (1, 0, 5, 1)}, ["B", "A", "C"]),
+    "BelowFairShare_UnevenCurrentCost": ({"A": (4, 2, 5, 2), "B": (3, 2, 5, 1), "C": (2, 1, 5, 1)}, ["C", "A", "B"]),
+    "AboveFairShare": ({"A": (8, 6, 5, 2), "B": (7, 4, 5, 3), "C": (9, 8, 5, 1)}, ["B", "A", "C"]),
+    "MixedFairShare": ({"A": (8, 6, 5, 2), "B": (3, 2, 5, 1)}, ["B", "A"]),
+    "Fallback": ({"B": (0, 0, 0, 0), "C": (0, 0, 0, 0), "A": (0, 0, 0, 0)}, ["A", "B", "C"]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PQ_ORDER))
+def test_queue_candidate_gang_iterator_pq_ordering(name):
+    """TestQueueCandidateGangIteratorPQ_Ordering_* / _Fallback: the oracle's Less, sorted like sort.Sort."""
+    import functools
+    lib = oracle_lib.load()
+    lib.armada_oracle_pq_less.argtypes = [C.c_int32, C.c_int32, abi.f64p, abi.f64p]
+    lib.armada_oracle_pq_less.restype = C.c_int32
+    items, want = PQ_ORDER[name]
+    rank = {q: i for i, q in enumerate(sorted(items))}
+
+    def vec(q):
+        return np.array(list(items[q]) + [rank[q], 0], np.float64)
+
+    def cmp(a, b):
+        if lib.armada_oracle_pq_less(1, 0, vec(a).ctypes.data_as(abi.f64p), vec(b).ctypes.data_as(abi.f64p)):
+            return -1
+        if lib.armada_oracle_pq_less(1, 0, vec(b).ctypes.data_as(abi.f64p), vec(a).ctypes.data_as(abi.f64p)):
+            return 1
+        return 0
+
+    assert sorted(items, key=functools.cmp_to_key(cmp)) == want
