@@ -65,3 +65,42 @@ def test_product_fails_loudly_without_a_device():
         DeviceRound(0)
     assert ei.value.status in (abi.E_NO_DEVICE, abi.E_CUDA)
 
+
+
+def test_header_is_plain_c99_and_a_c_caller_links(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (what cgo's C compiler sees), a C translation unit that
+    fills the structs and calls an entry point links against the product library, and the field offsets a C
+    compiler computes are the ones the ctypes mirror uses."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    fields = [("ArmadaRoundInput", "queued_order", abi.RoundInput.queued_order.offset),
+              ("ArmadaRoundInput", "gang_uniformity_label", abi.RoundInput.gang_uniformity_label.offset),
+              ("ArmadaRoundInput", "floating_limit", abi.RoundInput.floating_limit.offset),
+              ("ArmadaRoundOutput", "job_reason_first_pass", abi.RoundOutput.job_reason_first_pass.offset),
+              ("ArmadaRoundOutput", "num_result_preempted", abi.RoundOutput.num_result_preempted.offset),
+              ("ArmadaRoundStats", "batch_debug", abi.RoundStats.batch_debug.offset)]
+    checks = "\n".join(f'  if (offsetof({t}, {f}) != {off}) {{ printf("{t}.{f} %zu != {off}\\n", offsetof({t}, {f})); bad = 1; }}' for t, f, off in fields)
+    src.write_text(f'''#include <stddef.h>
+#include <stdio.h>
+#include "armada_b200.h"
+int main(void) {{
+  int bad = 0;
+{checks}
+  ArmadaRoundInput in = {{0}};
+  in.abi_version = ARMADA_ABI_VERSION;
+  if (armada_abi_version() != in.abi_version) bad = 1;
+  if (armada_abi_sizeof(0) != sizeof(ArmadaRoundInput)) bad = 1;
+  return bad;
+}}
+''')
+    exe = tmp_path / "caller"
+    if not os.path.exists(abi.PRODUCT_LIB_PATH):
+        pytest.skip("libarmada_b200.so not built")
+    libdir = os.path.dirname(abi.PRODUCT_LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-larmada_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
