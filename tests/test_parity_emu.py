@@ -497,3 +497,27 @@ def test_uniformity_rounds_with_large_and_running_gangs(seed):
     got, want = assert_parity(b.input, f"large / running uniformity gangs {seed}")
     if seed >= 52:
         assert int(want.stats.evicted_pass1) > 0  # the running gangs are evicted and go through the search pinned
+
+
+def test_dry_run_nodedb_ignores_floating_resources_in_the_node_fit():
+    """SubmitChecker's NodeDb with a floating resource in the factory: a job's floating request is no part of the node
+    fit (KubernetesResourceRequirements) — oracle and device agree, and the job fits where its cpu / memory do."""
+    from armada_b200.scheduler import DeviceNodeDb
+
+    class _R:  # what _dry_run_case needs of a round
+        def __init__(self, b):
+            self.b, self.job_class = b, b.job_class
+
+        def to_input(self):
+            return self.b.input
+
+    from armada_b200.model import RoundInputBuilder
+    b0 = gang_cases.uniformity_round(3, n_nodes=12, n_jobs=80, floating=True)
+    # (the SubmitChecker's NodeDb is the EMPTY cluster: no running jobs in the input)
+    b = RoundInputBuilder(b0.cfg, b0.nodes, [j for j in b0.jobs if j.node is None], b0.queues)
+    J = len(b.jobs)
+    with_lic = [j for j in range(J) if "licences" in b.jobs[j].requests and b.jobs[j].node is None]
+    assert with_lic
+    gangs = [[j] for j in with_lic[:10]] + [[j] for j in range(J) if b.jobs[j].node is None][:10]
+    oks = _dry_run_case(_R(b), gangs, emu_lib.load())
+    assert all(oks[: len(with_lic[:10])])  # 1–16 cpu on 32-cpu nodes of an empty cluster: every one fits
